@@ -1,0 +1,855 @@
+"""Host-side ``NetworkStructure`` container — drop-in for ``cityseer.rustalgos.graph.NetworkStructure`` on the
+centrality hot path (stub: /root/reference/pysrc/cityseer/rustalgos/graph.pyi:85-674; Rust: rust/src/graph.rs).
+
+The container keeps the node / edge payload fields the kernels read (graph.rs:25-38, :89-115) in plain Python lists
+with petgraph ``StableGraph`` index semantics (stable indices, LIFO free-lists, newest-first adjacency), freezes them
+into flat arrays on the first compute call, and hands those arrays to the CUDA library through the C ABI
+(``include/cityseer_b200.h``).  Compute methods never run on the CPU: without the CUDA library / a GPU they raise.
+"""
+from __future__ import annotations
+
+import math
+import re
+import threading
+from typing import Any
+
+import numpy as np
+
+from .. import _native
+from . import centrality as _centrality
+
+_NUM_RE = re.compile(r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?|[-+]?(?:inf|nan)", re.IGNORECASE)
+
+
+class NodeVisit:
+    """graph.rs:252-284"""
+
+    __slots__ = ("visited", "discovered", "pred", "short_dist", "simpl_dist", "origin_seg", "last_seg", "agg_seconds")
+
+    def __init__(self):
+        self.visited = False
+        self.discovered = False
+        self.pred = None
+        self.short_dist = math.inf
+        self.simpl_dist = math.inf
+        self.origin_seg = None
+        self.last_seg = None
+        self.agg_seconds = math.inf
+
+
+class EdgeVisit:
+    """graph.rs:287-315"""
+
+    __slots__ = ("visited", "start_nd_idx", "end_nd_idx", "edge_idx")
+
+    def __init__(self):
+        self.visited = False
+        self.start_nd_idx = None
+        self.end_nd_idx = None
+        self.edge_idx = None
+
+
+class NodePayload:
+    """graph.rs:25-38 (street nodes only; transport nodes are out of scope)."""
+
+    __slots__ = ("node_key", "x", "y", "z", "live", "weight", "is_transport")
+
+    def __init__(self, node_key, x, y, z, live, weight):
+        self.node_key = node_key
+        self.x = x
+        self.y = y
+        self.z = z
+        self.live = live
+        self.weight = weight
+        self.is_transport = False
+
+    @property
+    def coord(self):
+        return (self.x, self.y)
+
+    @property
+    def coord_z(self):
+        return (self.x, self.y, self.z)
+
+    def validate(self):
+        if not math.isfinite(self.weight) or self.weight < 0.0:
+            raise ValueError(
+                "Invalid street node payload: weight must be finite and non-negative (>= 0.0). "
+                f"Found {self.weight}. Node key: {self.node_key!r}"
+            )
+
+
+class EdgePayload:
+    """graph.rs:89-115 (street edges)."""
+
+    __slots__ = (
+        "start_nd_key_py", "end_nd_key_py", "shared_primal_node_key", "edge_idx", "length", "angle_sum", "imp_factor",
+        "in_bearing", "out_bearing", "seconds", "geom_wkt", "is_transport", "_src", "_dst", "_stamp",
+    )  # fmt: skip
+
+    def validate(self):
+        if not math.isfinite(self.imp_factor) or self.imp_factor <= 0.0:
+            raise ValueError(
+                f"Invalid edge payload : imp_factor must be finite and positive (> 0.0). Found {self.imp_factor}. "
+                f"Start key: {self.start_nd_key_py!r}, End key: {self.end_nd_key_py!r}"
+            )
+        if not math.isfinite(self.length):
+            raise ValueError(f"Invalid street edge payload : length must be finite. Found {self.length}.")
+        if not math.isfinite(self.angle_sum):
+            raise ValueError(f"Invalid street edge payload : angle_sum must be finite. Found {self.angle_sum}.")
+
+
+def parse_linestring_wkt(geom_wkt: str) -> list[tuple[float, float]]:
+    """Minimal WKT ``LINESTRING`` reader (2D or Z; Z is dropped, as geo's ``LineString<f64>`` is 2D)."""
+    s = geom_wkt.strip()
+    head = s[:12].upper()
+    if not head.startswith("LINESTRING"):
+        raise ValueError(f"expected LINESTRING, found: {s[:40]}")
+    lp = s.find("(")
+    rp = s.rfind(")")
+    if lp < 0 or rp < lp:
+        if "EMPTY" in s.upper():
+            return []
+        raise ValueError("malformed WKT")
+    has_z = " Z" in s[:lp].upper() or "Z(" in s[: lp + 1].upper()
+    coords = []
+    for part in s[lp + 1 : rp].split(","):
+        nums = _NUM_RE.findall(part)
+        if len(nums) < 2:
+            raise ValueError(f"malformed coordinate '{part.strip()}'")
+        if not has_z and len(nums) > 3:
+            raise ValueError(f"malformed coordinate '{part.strip()}'")
+        coords.append((float(nums[0]), float(nums[1])))
+    return coords
+
+
+def _bearing(ax, ay, bx, by) -> float:
+    # graph.rs:326-332
+    if ax == bx and ay == by:
+        return 0.0
+    return math.degrees(math.atan2(by - ay, bx - ax))
+
+
+def _coords_angle(a, b, c) -> float:
+    # graph.rs:336-346
+    if a == b or b == c:
+        return 0.0
+    a1 = _bearing(b[0], b[1], a[0], a[1])
+    a2 = _bearing(c[0], c[1], b[0], b[1])
+    diff = a2 - a1
+    # rem_euclid(360)
+    norm = math.fmod(diff + 180.0, 360.0)
+    if norm < 0.0:
+        norm += 360.0
+    return abs(norm - 180.0)
+
+
+def linestring_metrics(coords: list[tuple[float, float]]) -> tuple[float, float, float, float]:
+    """(length f32, angle_sum f32, in_bearing f32, out_bearing f32) per graph.rs:774-857."""
+    length = 0.0
+    for i in range(len(coords) - 1):
+        length += math.hypot(coords[i + 1][0] - coords[i][0], coords[i + 1][1] - coords[i][1])
+    angle_sum = 0.0
+    for i in range(1, len(coords) - 1):
+        angle_sum += _coords_angle(coords[i - 1], coords[i], coords[i + 1])
+    in_b = math.nan
+    first = coords[0]
+    for i in range(1, len(coords)):
+        if coords[i] != first:
+            in_b = _bearing(first[0], first[1], coords[i][0], coords[i][1])
+            break
+    if math.isnan(in_b):
+        in_b = 0.0
+    out_b = math.nan
+    last = coords[-1]
+    for i in range(len(coords) - 2, -1, -1):
+        if coords[i] != last:
+            out_b = _bearing(coords[i][0], coords[i][1], last[0], last[1])
+            break
+    if math.isnan(out_b):
+        out_b = 0.0
+    f32 = np.float32
+    return float(f32(length)), float(f32(angle_sum)), float(f32(in_b)), float(f32(out_b))
+
+
+class FrozenGraph:
+    """Flat arrays handed to the C ABI (and, in tests, to the oracle). Indexed by petgraph node / edge index."""
+
+    __slots__ = (
+        "node_bound", "node_exists", "live", "weight", "z", "edge_bound", "edge_exists", "src", "dst", "edge_idx",
+        "length", "angle_sum", "imp", "seconds", "shared_key", "stamp", "is_dual", "node_indices", "key_names",
+    )  # fmt: skip
+
+
+class NetworkStructure:
+    """Drop-in for ``cityseer.rustalgos.graph.NetworkStructure`` (centrality surface)."""
+
+    def __init__(self):
+        self._nodes: list[NodePayload | None] = []
+        self._free_nodes: list[int] = []
+        self._edges: list[EdgePayload | None] = []
+        self._free_edges: list[int] = []
+        self._out: list[list[int]] = []  # per node: edge ids, oldest first (iterate reversed = petgraph order)
+        self._in: list[list[int]] = []
+        self._stamp = 0
+        self._is_dual = False
+        self._progress = _native.ProgressCounter()
+        self._frozen: FrozenGraph | None = None
+        self._bulk: FrozenGraph | None = None  # set by from_arrays(); immutable bulk-ingested graph
+        self._bulk_keys = None
+        self._device = None  # _native.DeviceGraph
+        self._lock = threading.Lock()
+
+    # ------------------------------------------------------------------ basic state
+    def progress_init(self) -> None:
+        self._progress.set(0)
+
+    def progress(self) -> int:
+        return self._progress.get()
+
+    @property
+    def is_dual(self) -> bool:
+        return self._is_dual
+
+    def set_is_dual(self, is_dual: bool) -> None:
+        self._is_dual = bool(is_dual)
+        self._invalidate()
+
+    def _invalidate(self) -> None:
+        if self._bulk is not None:
+            raise ValueError("NetworkStructure built with from_arrays() is immutable.")
+        self._frozen = None
+        if self._device is not None:
+            self._device.close()
+            self._device = None
+
+    # ------------------------------------------------------------------ nodes
+    def add_street_node(self, node_key, x: float, y: float, live: bool, weight: float, z: float | None = None) -> int:
+        """graph.rs:427-452"""
+        payload = NodePayload(node_key, float(x), float(y), None if z is None else float(z), bool(live),
+                              float(np.float32(weight)))  # fmt: skip
+        payload.validate()
+        self._invalidate()
+        if self._free_nodes:
+            idx = self._free_nodes.pop()
+            self._nodes[idx] = payload
+        else:
+            idx = len(self._nodes)
+            self._nodes.append(payload)
+            self._out.append([])
+            self._in.append([])
+        return idx
+
+    def add_transport_node(self, *args, **kwargs):
+        raise NotImplementedError("transport nodes are outside the centrality hot path (SURVEY.md §8f-4)")
+
+    def add_transport_edge(self, *args, **kwargs):
+        raise NotImplementedError("transport edges are outside the centrality hot path (SURVEY.md §8f-4)")
+
+    def _require_node(self, node_idx: int, param: str) -> NodePayload:
+        # graph.rs:1248-1258
+        if self._bulk is not None:
+            raise ValueError("per-node payload access is not available on a from_arrays() graph")
+        if node_idx < 0 or node_idx >= len(self._nodes) or self._nodes[node_idx] is None:
+            raise ValueError(f"{param} {node_idx} does not exist in the graph.")
+        return self._nodes[node_idx]  # type: ignore[return-value]
+
+    def get_node_payload_py(self, node_idx: int) -> NodePayload:
+        return self._require_node(node_idx, "node_idx")
+
+    def get_node_weight(self, node_idx: int) -> float:
+        if self._bulk is not None:
+            self._check_bulk_node(node_idx)
+            return float(self._bulk.weight[node_idx])
+        return self._require_node(node_idx, "node_idx").weight
+
+    def is_node_live(self, node_idx: int) -> bool:
+        if self._bulk is not None:
+            self._check_bulk_node(node_idx)
+            return bool(self._bulk.live[node_idx])
+        return self._require_node(node_idx, "node_idx").live
+
+    def _check_bulk_node(self, node_idx: int) -> None:
+        if node_idx < 0 or node_idx >= self._bulk.node_bound:
+            raise ValueError(f"node_idx {node_idx} does not exist in the graph.")
+
+    def set_node_live(self, node_idx: int, live: bool) -> None:
+        if self._bulk is not None:
+            raise ValueError("NetworkStructure built with from_arrays() is immutable.")
+        if node_idx < 0 or node_idx >= len(self._nodes) or self._nodes[node_idx] is None:
+            raise ValueError(f"Node index {node_idx} does not exist in the graph.")
+        self._nodes[node_idx].live = bool(live)  # type: ignore[union-attr]
+        self._invalidate()
+
+    def remove_street_node(self, node_idx: int) -> None:
+        """graph.rs:893-913; petgraph StableGraph::remove_node (out-edges then in-edges, newest first)."""
+        if node_idx < 0 or node_idx >= len(self._nodes) or self._nodes[node_idx] is None:
+            raise ValueError(f"Node index {node_idx} does not exist in the graph.")
+        self._invalidate()
+        for lst in (self._out, self._in):
+            while lst[node_idx]:
+                self._remove_edge_id(lst[node_idx][-1])
+        self._nodes[node_idx] = None
+        self._free_nodes.append(node_idx)
+
+    def node_count(self) -> int:
+        if self._bulk is not None:
+            return int(self._bulk.node_exists.sum())
+        return len(self._nodes) - len(self._free_nodes)
+
+    def node_bound(self) -> int:
+        if self._bulk is not None:
+            return self._bulk.node_bound
+        n = len(self._nodes)
+        while n > 0 and self._nodes[n - 1] is None:
+            n -= 1
+        return n
+
+    def edge_bound(self) -> int:
+        if self._bulk is not None:
+            return self._bulk.edge_bound
+        n = len(self._edges)
+        while n > 0 and self._edges[n - 1] is None:
+            n -= 1
+        return n
+
+    def street_node_count(self) -> int:
+        return self.node_count()
+
+    def node_indices(self) -> list[int]:
+        if self._bulk is not None:
+            return self._bulk.node_indices.tolist()
+        return [i for i, p in enumerate(self._nodes) if p is not None]
+
+    def street_node_indices(self) -> list[int]:
+        return self.node_indices()
+
+    def node_keys_py(self) -> list[Any]:
+        if self._bulk is not None:
+            if self._bulk_keys is None:
+                return self._bulk.node_indices.tolist()
+            return list(self._bulk_keys)
+        return [p.node_key for p in self._nodes if p is not None]
+
+    @property
+    def node_xs(self) -> list[float]:
+        return [p.x for p in self._nodes if p is not None]
+
+    @property
+    def node_ys(self) -> list[float]:
+        return [p.y for p in self._nodes if p is not None]
+
+    @property
+    def node_xys(self) -> list[tuple[float, float]]:
+        return [(p.x, p.y) for p in self._nodes if p is not None]
+
+    @property
+    def node_zs(self) -> list[float | None]:
+        return [p.z for p in self._nodes if p is not None]
+
+    @property
+    def node_lives(self) -> list[bool]:
+        if self._bulk is not None:
+            return self._bulk.live[self._bulk.node_indices].astype(bool).tolist()
+        return [p.live for p in self._nodes if p is not None]
+
+    @property
+    def street_node_lives(self) -> list[bool]:
+        return self.node_lives
+
+    # ------------------------------------------------------------------ edges
+    @property
+    def edge_count(self) -> int:
+        if self._bulk is not None:
+            return int(self._bulk.edge_exists.sum())
+        return len(self._edges) - len(self._free_edges)
+
+    def add_street_edge(
+        self,
+        start_nd_idx: int,
+        end_nd_idx: int,
+        edge_idx: int,
+        start_nd_key_py,
+        end_nd_key_py,
+        geom_wkt: str,
+        imp_factor: float | None = None,
+        shared_primal_node_key: str | None = None,
+    ) -> int:
+        """graph.rs:728-889 — WKT → length / bearings / angle_sum (f64 → f32); ``seconds`` = NaN."""
+        wkt_preview = geom_wkt if len(geom_wkt) <= 200 else f"{geom_wkt[:200]}... (truncated, {len(geom_wkt)} chars total)"
+        try:
+            coords = parse_linestring_wkt(geom_wkt)
+        except ValueError as e:
+            raise ValueError(
+                f"Failed to parse WKT for street edge (idx {edge_idx}) between nodes {start_nd_idx} and {end_nd_idx}.\n"
+                f"Parse error: {e}\nWKT: {wkt_preview}"
+            ) from None
+        if len(coords) < 2:
+            raise ValueError(
+                f"Street edge geometry (idx {edge_idx}) between nodes {start_nd_idx} and {end_nd_idx} must have at "
+                f"least 2 coordinates. Found {len(coords)}.\nWKT: {wkt_preview}"
+            )
+        length, angle_sum, in_b, out_b = linestring_metrics(coords)
+        imp = 1.0 if imp_factor is None else float(np.float32(imp_factor))
+        if not math.isfinite(imp) or imp <= 0.0:
+            raise ValueError(
+                f"Invalid impedance factor ({imp}) for edge (idx {edge_idx}) between nodes {start_nd_idx} and "
+                f"{end_nd_idx}.\nImpedance must be finite and positive (> 0.0).\n"
+                f"Edge length: {length:.4f}m, num_coords: {len(coords)}"
+            )
+        p = EdgePayload()
+        p.start_nd_key_py = start_nd_key_py
+        p.end_nd_key_py = end_nd_key_py
+        p.shared_primal_node_key = None if shared_primal_node_key is None else str(shared_primal_node_key)
+        p.edge_idx = int(edge_idx)
+        p.length = length
+        p.angle_sum = angle_sum
+        p.imp_factor = imp
+        p.in_bearing = in_b
+        p.out_bearing = out_b
+        p.seconds = math.nan
+        p.geom_wkt = geom_wkt
+        p.is_transport = False
+        return self._add_edge_internal(start_nd_idx, end_nd_idx, p)
+
+    def _add_edge_internal(self, start_nd_idx: int, end_nd_idx: int, p: EdgePayload) -> int:
+        self._require_node(start_nd_idx, "start_nd_idx")
+        self._require_node(end_nd_idx, "end_nd_idx")
+        p.validate()
+        self._invalidate()
+        p._src = start_nd_idx
+        p._dst = end_nd_idx
+        self._stamp += 1
+        p._stamp = self._stamp
+        if self._free_edges:
+            eid = self._free_edges.pop()
+            self._edges[eid] = p
+        else:
+            eid = len(self._edges)
+            self._edges.append(p)
+        self._out[start_nd_idx].append(eid)
+        self._in[end_nd_idx].append(eid)
+        return eid
+
+    def _remove_edge_id(self, eid: int) -> None:
+        p = self._edges[eid]
+        self._out[p._src].remove(eid)
+        self._in[p._dst].remove(eid)
+        self._edges[eid] = None
+        self._free_edges.append(eid)
+
+    def _find_edge(self, start_nd_idx: int, end_nd_idx: int, edge_idx: int) -> int | None:
+        # petgraph edges_connecting: out-list order, newest first
+        for eid in reversed(self._out[start_nd_idx]):
+            p = self._edges[eid]
+            if p._dst == end_nd_idx and p.edge_idx == edge_idx:
+                return eid
+        return None
+
+    def remove_street_edge(self, start_nd_idx: int, end_nd_idx: int, edge_idx: int) -> None:
+        """graph.rs:917-943"""
+        self._require_node(start_nd_idx, "start_nd_idx")
+        self._require_node(end_nd_idx, "end_nd_idx")
+        eid = self._find_edge(start_nd_idx, end_nd_idx, edge_idx)
+        if eid is None:
+            raise ValueError(
+                f"No edge with edge_idx {edge_idx} found from node {start_nd_idx} to node {end_nd_idx}."
+            )
+        self._invalidate()
+        self._remove_edge_id(eid)
+
+    def edge_references(self) -> list[tuple[int, int, int]]:
+        if self._bulk is not None:
+            b = self._bulk
+            return list(zip(b.src.tolist(), b.dst.tolist(), b.edge_idx.tolist()))
+        return [(p._src, p._dst, p.edge_idx) for p in self._edges if p is not None]
+
+    def _edge_payload_checked(self, s: int, e: int, k: int) -> EdgePayload:
+        self._require_node(s, "start_nd_idx")
+        self._require_node(e, "end_nd_idx")
+        eid = self._find_edge(s, e, k)
+        if eid is None:
+            raise ValueError("Edge not found")
+        return self._edges[eid]  # type: ignore[return-value]
+
+    def get_edge_payload_py(self, start_nd_idx: int, end_nd_idx: int, edge_idx: int) -> EdgePayload:
+        return self._edge_payload_checked(start_nd_idx, end_nd_idx, edge_idx)
+
+    def get_edge_length(self, start_nd_idx: int, end_nd_idx: int, edge_idx: int) -> float:
+        return self._edge_payload_checked(start_nd_idx, end_nd_idx, edge_idx).length
+
+    def get_edge_impedance(self, start_nd_idx: int, end_nd_idx: int, edge_idx: int) -> float:
+        return self._edge_payload_checked(start_nd_idx, end_nd_idx, edge_idx).imp_factor
+
+    def validate(self) -> None:
+        """graph.rs:1035-1058"""
+        if self.node_count() == 0:
+            raise ValueError("NetworkStructure contains no nodes.")
+        if self._bulk is not None:
+            return
+        for p in self._nodes:
+            if p is not None:
+                p.validate()
+        for e in self._edges:
+            if e is not None:
+                e.validate()
+
+    def build_edge_rtree(self) -> None:
+        """The edge R-tree serves land-use assignment only (graph.rs:1064-1232) — not on this path; no-op."""
+
+    # ------------------------------------------------------------------ bulk ingest
+    @classmethod
+    def from_arrays(
+        cls,
+        *,
+        live,
+        weight,
+        src,
+        dst,
+        edge_idx,
+        length,
+        angle_sum=None,
+        imp_factor=None,
+        z=None,
+        shared_key=None,
+        is_dual: bool = False,
+        node_keys=None,
+    ) -> "NetworkStructure":
+        """Array ingest: the same container state as ``add_street_node`` × N then ``add_street_edge`` × E called in
+        array order (directed edges; pass both directions), with ``length`` / ``angle_sum`` already measured.
+        ``shared_key`` is an int32 id per edge (dual graphs; equal ids = equal ``shared_primal_node_key``)."""
+        self = cls()
+        f = FrozenGraph()
+        n = len(live)
+        e = len(src)
+        f.node_bound = n
+        f.node_exists = np.ones(n, dtype=np.uint8)
+        f.live = np.ascontiguousarray(live, dtype=np.uint8)
+        f.weight = np.ascontiguousarray(weight, dtype=np.float32)
+        f.z = np.full(n, np.nan, dtype=np.float64) if z is None else np.ascontiguousarray(z, dtype=np.float64)
+        f.edge_bound = e
+        f.edge_exists = np.ones(e, dtype=np.uint8)
+        f.src = np.ascontiguousarray(src, dtype=np.uint32)
+        f.dst = np.ascontiguousarray(dst, dtype=np.uint32)
+        f.edge_idx = np.ascontiguousarray(edge_idx, dtype=np.uint32)
+        f.length = np.ascontiguousarray(length, dtype=np.float32)
+        f.angle_sum = np.zeros(e, np.float32) if angle_sum is None else np.ascontiguousarray(angle_sum, dtype=np.float32)
+        f.imp = np.ones(e, np.float32) if imp_factor is None else np.ascontiguousarray(imp_factor, dtype=np.float32)
+        f.seconds = np.full(e, np.nan, dtype=np.float32)
+        f.shared_key = np.full(e, -1, np.int32) if shared_key is None else np.ascontiguousarray(shared_key, dtype=np.int32)
+        f.stamp = np.arange(1, e + 1, dtype=np.uint64)
+        f.is_dual = bool(is_dual)
+        f.node_indices = np.arange(n, dtype=np.int64)
+        f.key_names = None
+        if e and (int(f.src.max()) >= n or int(f.dst.max()) >= n):
+            raise ValueError("edge endpoint index out of range")
+        if not np.all(np.isfinite(f.weight)) or np.any(f.weight < 0):
+            raise ValueError("Invalid street node payload: weight must be finite and non-negative (>= 0.0).")
+        if not np.all(np.isfinite(f.imp)) or np.any(f.imp <= 0):
+            raise ValueError("Invalid edge payload : imp_factor must be finite and positive (> 0.0).")
+        if not np.all(np.isfinite(f.length)) or not np.all(np.isfinite(f.angle_sum)):
+            raise ValueError("Invalid street edge payload : length and angle_sum must be finite.")
+        self._is_dual = bool(is_dual)
+        self._bulk = f
+        self._frozen = f
+        self._bulk_keys = None if node_keys is None else list(node_keys)
+        return self
+
+    # ------------------------------------------------------------------ freeze → flat arrays
+    def frozen(self) -> FrozenGraph:
+        """Flat arrays in petgraph index order; cached until the next mutation."""
+        if self._frozen is not None:
+            return self._frozen
+        f = FrozenGraph()
+        nb = self.node_bound()
+        eb = self.edge_bound()
+        f.node_bound = nb
+        f.node_exists = np.zeros(nb, np.uint8)
+        f.live = np.zeros(nb, np.uint8)
+        f.weight = np.zeros(nb, np.float32)
+        f.z = np.full(nb, np.nan, np.float64)
+        for i in range(nb):
+            p = self._nodes[i]
+            if p is None:
+                continue
+            f.node_exists[i] = 1
+            f.live[i] = 1 if p.live else 0
+            f.weight[i] = p.weight
+            if p.z is not None:
+                f.z[i] = p.z
+        f.edge_bound = eb
+        f.edge_exists = np.zeros(eb, np.uint8)
+        f.src = np.zeros(eb, np.uint32)
+        f.dst = np.zeros(eb, np.uint32)
+        f.edge_idx = np.zeros(eb, np.uint32)
+        f.length = np.zeros(eb, np.float32)
+        f.angle_sum = np.zeros(eb, np.float32)
+        f.imp = np.ones(eb, np.float32)
+        f.seconds = np.full(eb, np.nan, np.float32)
+        f.shared_key = np.full(eb, -1, np.int32)
+        f.stamp = np.zeros(eb, np.uint64)
+        key_ids: dict[str, int] = {}
+        for i in range(eb):
+            e = self._edges[i]
+            if e is None:
+                continue
+            f.edge_exists[i] = 1
+            f.src[i] = e._src
+            f.dst[i] = e._dst
+            f.edge_idx[i] = e.edge_idx
+            f.length[i] = e.length
+            f.angle_sum[i] = e.angle_sum
+            f.imp[i] = e.imp_factor
+            f.seconds[i] = e.seconds
+            f.stamp[i] = e._stamp
+            if e.shared_primal_node_key is not None:
+                f.shared_key[i] = key_ids.setdefault(e.shared_primal_node_key, len(key_ids))
+        f.is_dual = self._is_dual
+        f.node_indices = np.nonzero(f.node_exists)[0].astype(np.int64)
+        f.key_names = key_ids
+        self._frozen = f
+        return f
+
+    def device_graph(self):
+        """Upload (once) and return the device-resident graph handle. Raises if the CUDA library / GPU is missing."""
+        with self._lock:
+            if self._device is None:
+                self._device = _native.DeviceGraph(self.frozen())
+            return self._device
+
+    # ------------------------------------------------------------------ sampling plan (centrality.rs:1032-1139)
+    def _expand_sampling_weights(self, weights) -> np.ndarray:
+        w = np.asarray(weights, dtype=np.float32)
+        nc, nb = self.node_count(), self.node_bound()
+        if len(w) != nb and len(w) != nc:
+            raise ValueError(f"sampling_weights length ({len(w)}) must match node_count ({nc}) or node_bound ({nb})")
+        bad = np.nonzero((w < 0.0) | (w > 1.0))[0]
+        if len(bad):
+            i = int(bad[0])
+            raise ValueError(f"sampling_weights[{i}] = {w[i]} is out of range [0.0, 1.0]")
+        if len(w) == nb:
+            return w.copy()
+        out = np.zeros(nb, np.float32)
+        out[np.asarray(self.node_indices(), dtype=np.int64)] = w
+        return out
+
+    def _prepare_sources(self, sample_probability, sampling_weights, random_seed, source_indices):
+        """Returns (sources u32[], wt f32[], eligible u8[node_bound], n_visited_for_progress, is_sampled, scale)."""
+        f = self.frozen()
+        nb = f.node_bound
+        sw = None if sampling_weights is None else self._expand_sampling_weights(sampling_weights)
+        if sample_probability is not None:
+            sample_probability = float(np.float32(sample_probability))
+            if sample_probability <= 0.0 or sample_probability > 1.0:
+                raise ValueError("sample_probability must be in (0.0, 1.0]")
+        if source_indices is not None and sw is not None:
+            raise ValueError("source_indices and sampling_weights are mutually exclusive")
+        node_indices = f.node_indices
+        if source_indices is not None:
+            src = np.asarray(list(source_indices), dtype=np.int64)
+            for s in src.tolist():
+                if s < 0 or s >= nb or not f.node_exists[s]:
+                    raise ValueError(f"node index {s} does not exist in the graph")
+        live_mask = f.live.astype(bool) & f.node_exists.astype(bool)
+        n_live = int(live_mask[node_indices].sum())
+        eligible = np.zeros(nb, np.uint8)
+        is_indexed = source_indices is not None
+        if is_indexed:
+            sources_all = src
+            eligible[src] = 1
+        else:
+            sources_all = node_indices
+            eligible[live_mask] = 1
+        n_sources = len(sources_all)
+        wt_all = f.weight[sources_all].astype(np.float32)
+        keep = eligible[sources_all].astype(bool)
+        if is_indexed:
+            if sample_probability is not None:
+                wt_all = (wt_all / np.float32(sample_probability)).astype(np.float32)
+        elif sample_probability is not None:
+            # Bernoulli draw per node_bound slot. The reference draws from rand::StdRng (ChaCha12), whose stream is not
+            # pinned by any upstream test (only same-seed self-consistency is); we use numpy's PCG64 — SURVEY.md §8c.
+            rng = np.random.default_rng(random_seed)
+            randoms = rng.random(nb, dtype=np.float32)
+            p = np.full(nb, np.float32(sample_probability), np.float32)
+            if sw is not None:
+                p = (p * sw).astype(np.float32)
+            ps = p[sources_all]
+            keep &= (ps > 0.0) & (randoms[sources_all] < ps)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                wt_all = (wt_all / ps).astype(np.float32)
+        sources = np.ascontiguousarray(sources_all[keep], dtype=np.uint32)
+        wt = np.ascontiguousarray(wt_all[keep], dtype=np.float32)
+        tracked = sample_probability is not None or is_indexed
+        scale = 1.0
+        if is_indexed and sample_probability is None:
+            scale = n_live / n_sources if n_sources else 1.0
+        return sources, wt, eligible, n_sources, tracked, scale
+
+    # ------------------------------------------------------------------ compute entry points (CUDA only)
+    def centrality_shortest(
+        self,
+        distances=None,
+        betas=None,
+        minutes=None,
+        compute_closeness=None,
+        compute_betweenness=None,
+        min_threshold_wt=None,
+        speed_m_s=None,
+        tolerance=None,
+        sample_probability=None,
+        sampling_weights=None,
+        random_seed=None,
+        source_indices=None,
+        pbar_disabled=None,
+    ) -> "_centrality.CentralityShortestResult":
+        """centrality.rs:1624-1874 — one capped search per source on the GPU; closeness scattered to targets,
+        betweenness by reverse dependency accumulation; results summed into ``[7][D][node_bound]`` f64."""
+        from . import pair_distances_betas_time, WALKING_SPEED
+
+        compute_closeness = True if compute_closeness is None else bool(compute_closeness)
+        compute_betweenness = True if compute_betweenness is None else bool(compute_betweenness)
+        if not compute_closeness and not compute_betweenness:
+            raise ValueError(
+                "Either or both closeness and betweenness flags is required, but both parameters are False."
+            )
+        speed = float(WALKING_SPEED if speed_m_s is None else np.float32(speed_m_s))
+        tol = _centrality.validate_tolerance(tolerance)
+        d, b, s = pair_distances_betas_time(speed, distances, betas, minutes, min_threshold_wt)
+        sources, wt, eligible, n_prog, tracked, scale = self._prepare_sources(
+            sample_probability, sampling_weights, random_seed, source_indices
+        )
+        self.progress_init()
+        dev = self.device_graph()
+        out, stats = dev.centrality_shortest(
+            d, b, s, speed, tol, compute_closeness, compute_betweenness, sources, wt, eligible,
+            None if pbar_disabled else self._progress, n_prog,
+        )  # fmt: skip
+        if compute_betweenness and scale != 1.0:
+            out[5:7] *= scale
+        f = self.frozen()
+        res = _centrality.CentralityShortestResult(d, self.node_keys_py(), f.node_indices, out, stats)
+        if tracked:
+            res.sampled_source_count = int(len(sources))
+            res.reachability_totals = [int(x) for x in stats["reach_totals"]] if compute_closeness else [0] * len(d)
+        return res
+
+    def centrality_simplest(
+        self,
+        distances=None,
+        betas=None,
+        minutes=None,
+        compute_closeness=None,
+        compute_betweenness=None,
+        min_threshold_wt=None,
+        speed_m_s=None,
+        tolerance=None,
+        angular_scaling_unit=None,
+        farness_scaling_offset=None,
+        sample_probability=None,
+        sampling_weights=None,
+        random_seed=None,
+        source_indices=None,
+        pbar_disabled=None,
+    ) -> "_centrality.CentralitySimplestResult":
+        """centrality.rs:1880-2132 — angular (simplest-path) centrality on the dual graph."""
+        from . import pair_distances_betas_time, WALKING_SPEED
+
+        if not self._is_dual:
+            raise ValueError(
+                "centrality_simplest requires a dual graph for angular analysis. Convert the graph with "
+                "cityseer.tools.graphs.nx_to_dual(...) before ingesting it into NetworkStructure."
+            )
+        compute_closeness = True if compute_closeness is None else bool(compute_closeness)
+        compute_betweenness = True if compute_betweenness is None else bool(compute_betweenness)
+        tol = _centrality.validate_tolerance(tolerance)
+        if not compute_closeness and not compute_betweenness:
+            raise ValueError(
+                "Either or both closeness and betweenness flags is required, but both parameters are False."
+            )
+        speed = float(WALKING_SPEED if speed_m_s is None else np.float32(speed_m_s))
+        unit = float(np.float32(180.0 if angular_scaling_unit is None else angular_scaling_unit))
+        offset = float(np.float32(1.0 if farness_scaling_offset is None else farness_scaling_offset))
+        d, _b, s = pair_distances_betas_time(speed, distances, betas, minutes, min_threshold_wt)
+        sources, wt, eligible, n_prog, tracked, scale = self._prepare_sources(
+            sample_probability, sampling_weights, random_seed, source_indices
+        )
+        self.progress_init()
+        dev = self.device_graph()
+        out, stats = dev.centrality_simplest(
+            d, s, speed, tol, unit, offset, compute_closeness, compute_betweenness, sources, wt, eligible,
+            None if pbar_disabled else self._progress, n_prog,
+        )  # fmt: skip
+        if compute_betweenness and scale != 1.0:
+            out[3:4] *= scale
+        f = self.frozen()
+        res = _centrality.CentralitySimplestResult(d, self.node_keys_py(), f.node_indices, out, stats)
+        if tracked:
+            res.sampled_source_count = int(len(sources))
+            res.reachability_totals = [int(x) for x in stats["reach_totals"]] if compute_closeness else [0] * len(d)
+        return res
+
+    def segment_centrality(
+        self,
+        distances=None,
+        betas=None,
+        minutes=None,
+        compute_closeness=None,
+        compute_betweenness=None,
+        min_threshold_wt=None,
+        speed_m_s=None,
+        pbar_disabled=None,
+    ) -> "_centrality.CentralitySegmentResult":
+        """centrality.rs:2134-2407 — continuous (segment) closeness at the source + tree betweenness."""
+        from . import pair_distances_betas_time, WALKING_SPEED
+
+        speed = float(WALKING_SPEED if speed_m_s is None else np.float32(speed_m_s))
+        d, b, s = pair_distances_betas_time(speed, distances, betas, minutes, min_threshold_wt)
+        compute_closeness = True if compute_closeness is None else bool(compute_closeness)
+        compute_betweenness = True if compute_betweenness is None else bool(compute_betweenness)
+        if not compute_closeness and not compute_betweenness:
+            raise ValueError(
+                "Either or both closeness and betweenness flags is required, but both parameters are False."
+            )
+        f = self.frozen()
+        node_indices = f.node_indices
+        live = f.live[node_indices].astype(bool)
+        sources = np.ascontiguousarray(node_indices[live], dtype=np.uint32)
+        self.progress_init()
+        dev = self.device_graph()
+        out, stats = dev.segment_centrality(
+            d, b, s, speed, compute_closeness, compute_betweenness, sources,
+            None if pbar_disabled else self._progress, len(node_indices),
+        )  # fmt: skip
+        return _centrality.CentralitySegmentResult(d, self.node_keys_py(), f.node_indices, out, stats)
+
+    # ------------------------------------------------------------------ single-source tree searches
+    def _validate_dijkstra_inputs(self, src_idx: int, speed_m_s: float) -> None:
+        # centrality.rs:1009-1030
+        f = self.frozen()
+        if src_idx < 0 or src_idx >= f.node_bound:
+            raise ValueError(f"src_idx {src_idx} out of range for network with node_bound {f.node_bound}")
+        if not f.node_exists[src_idx]:
+            raise ValueError(f"src_idx {src_idx} does not exist in the graph")
+        if not math.isfinite(speed_m_s) or speed_m_s <= 0.0:
+            raise ValueError(f"speed_m_s must be finite and positive, got {speed_m_s}")
+
+    def dijkstra_tree_shortest(self, src_idx: int, max_seconds: int, speed_m_s: float):
+        """centrality.rs:1499-1508 — device search; returns ``(visited_nodes, tree_map)``."""
+        self._validate_dijkstra_inputs(src_idx, float(speed_m_s))
+        return self.device_graph().dijkstra_tree(0, src_idx, int(max_seconds), float(np.float32(speed_m_s)))
+
+    def dijkstra_tree_simplest(self, src_idx: int, max_seconds: int, speed_m_s: float):
+        """centrality.rs:1510-1521"""
+        if not self._is_dual:
+            raise ValueError(
+                "dijkstra_tree_simplest requires a dual graph for angular analysis. Convert the graph with "
+                "cityseer.tools.graphs.nx_to_dual(...) before ingesting it into NetworkStructure."
+            )
+        self._validate_dijkstra_inputs(src_idx, float(speed_m_s))
+        return self.device_graph().dijkstra_tree(1, src_idx, int(max_seconds), float(np.float32(speed_m_s)))
+
+    def dijkstra_tree_segment(self, src_idx: int, max_seconds: int, speed_m_s: float):
+        """centrality.rs:1523-1611"""
+        self._validate_dijkstra_inputs(src_idx, float(speed_m_s))
+        return self.device_graph().dijkstra_tree(2, src_idx, int(max_seconds), float(np.float32(speed_m_s)))

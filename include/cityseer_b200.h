@@ -1,0 +1,105 @@
+/* cityseer_b200 — C ABI of the B200-native localized-centrality hot path.
+ *
+ * This is the drop-in seam beneath cityseer's `NetworkStructure` operator API.  The reference crosses exactly one
+ * boundary on this path — Python -> PyO3 method on `rustalgos.graph.NetworkStructure`
+ * (/root/reference/rust/src/lib.rs:37-77, stubs in pysrc/cityseer/rustalgos/graph.pyi:85-674) — and every entry
+ * point below replaces one of those methods (file:line cited per function).  Plain pointers and sizes only; no
+ * Python / torch types.  All functions return 0 on success, non-zero on error; `cs_last_error()` returns a
+ * thread-local message.  There is no CPU fallback: every compute call requires a CUDA device (sm_100a build).
+ *
+ * Graph arrays are indexed by the reference's petgraph `StableGraph` indices (node index / edge index, gaps allowed):
+ * that is what `NetworkStructure.node_indices()` / `edge_references()` expose (graph.rs:613, :987).
+ */
+#ifndef CITYSEER_B200_H
+#define CITYSEER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cs_graph cs_graph;
+
+#define CS_MAX_THRESHOLDS 16 /* D, number of distance thresholds per call */
+#define CS_MAX_DEGREE 32     /* max in/out degree per node (predecessor sets are 32-bit adjacency masks) */
+
+/* Counters and timings of the last call (all totals over the sources this call processed). */
+typedef struct cs_stats {
+    uint64_t sources;         /* sources searched */
+    uint64_t settled;         /* nodes (states, for simplest) settled: sum over sources of R */
+    uint64_t edge_iters;      /* directed edges iterated at settled nodes (the reference's edges_directed loop trips) */
+    uint64_t sum_ri;          /* closeness: (source, target, threshold) triples accumulated */
+    uint64_t sum_ci;          /* betweenness: positive credits accumulated */
+    uint64_t relaxations;     /* device: successful distance decreases (work-efficiency of the label-correcting search) */
+    uint64_t reach_totals[CS_MAX_THRESHOLDS]; /* per-threshold reachable-target totals (centrality.rs:1743-1753) */
+    float kernel_ms;          /* CUDA-event time of the search/accumulate kernel on the launching stream */
+    float total_ms;           /* CUDA-event time incl. uploads of per-call arrays, zeroing and result download */
+    uint32_t gpu_launches;    /* kernels launched by this call */
+    uint32_t workers;         /* resident warps (one source per warp at a time) */
+} cs_stats;
+
+const char* cs_last_error(void);
+int cs_device_count(void);
+
+/* Replaces NetworkStructure construction + add_street_node / add_street_edge ingest (graph.rs:427-452, :728-889) and
+ * validate() (:1035-1058): takes the container's payload fields as flat arrays, builds both CSR orientations with
+ * 16-byte edge records in petgraph adjacency order (newest edge first), uploads once to `device`.
+ *   node arrays [node_bound]: exists, live, weight, z (NaN = no elevation)
+ *   edge arrays [edge_bound]: exists, src, dst, edge_idx (payload key), length, angle_sum, imp_factor,
+ *                             seconds (NaN for street edges), shared_key (dual: id of shared_primal_node_key, else -1),
+ *                             stamp (insertion sequence; larger = newer)
+ */
+cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_exists, const uint8_t* live, const float* weight,
+                          const double* z, uint64_t edge_bound, const uint8_t* edge_exists, const uint32_t* src,
+                          const uint32_t* dst, const uint32_t* edge_idx, const float* length, const float* angle_sum,
+                          const float* imp_factor, const float* seconds, const int32_t* shared_key,
+                          const uint64_t* stamp, int is_dual, int device);
+void cs_graph_destroy(cs_graph* g);
+
+/* Tunables (0 = keep default): arena capacity in reached nodes per source, near/far bucket width in seconds,
+ * resident warps.  */
+int cs_graph_configure(cs_graph* g, uint32_t reach_capacity, float delta_seconds, uint32_t workers);
+
+/* Replaces NetworkStructure.centrality_shortest (centrality.rs:1624-1874) after threshold pairing and source planning
+ * (which stay on the host: common.rs:239-270, centrality.rs:1032-1139).
+ *   distances/betas/seconds [D]   paired thresholds
+ *   tolerance                     fraction, >= 1e-4 (validate_tolerance, centrality.rs:34-48)
+ *   sources/source_wt [n_sources] eligible sources to search and their weight (node weight / sampling p)
+ *   eligible [node_bound]         source_eligible mask (pair weight 0.5 vs 1.0, centrality.rs:1802-1806)
+ *   out                           double [7][D][node_bound]: density, farness, cycles, harmonic, beta,
+ *                                 betweenness, betweenness_beta.  Host pointer, or device pointer if out_on_device.
+ *   accumulate                    0: out is overwritten; 1: added into (device pointer only; multi-call accumulation)
+ */
+int cs_centrality_shortest(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
+                           float speed_m_s, float tolerance, int compute_closeness, int compute_betweenness,
+                           uint64_t n_sources, const uint32_t* sources, const float* source_wt, const uint8_t* eligible,
+                           double* out, int out_on_device, int accumulate, cs_stats* stats);
+
+/* Replaces NetworkStructure.centrality_simplest (centrality.rs:1880-2132). out: double [4][D][node_bound]:
+ * density, farness, harmonic, betweenness. */
+int cs_centrality_simplest(cs_graph* g, int D, const uint32_t* distances, const uint32_t* seconds, float speed_m_s,
+                           float tolerance, float angular_scaling_unit, float farness_scaling_offset,
+                           int compute_closeness, int compute_betweenness, uint64_t n_sources, const uint32_t* sources,
+                           const float* source_wt, const uint8_t* eligible, double* out, int out_on_device,
+                           int accumulate, cs_stats* stats);
+
+/* Replaces NetworkStructure.segment_centrality (centrality.rs:2134-2407). out: double [4][D][node_bound]:
+ * segment density, harmonic, beta, betweenness. */
+int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
+                          float speed_m_s, int compute_closeness, int compute_betweenness, uint64_t n_sources,
+                          const uint32_t* sources, double* out, int out_on_device, int accumulate, cs_stats* stats);
+
+/* Replaces NetworkStructure.progress() (graph.rs:413): sources finished by the call in flight on this graph
+ * (readable from another host thread while a compute call blocks). */
+uint64_t cs_progress(cs_graph* g);
+
+/* Per-source search dump for distance-level parity tests (no reference counterpart; mirrors what
+ * dijkstra_brandes_shortest leaves in BrandesTraversal, centrality.rs:418-424): arrays sized node_bound. */
+int cs_shortest_search(cs_graph* g, uint32_t src, uint32_t max_seconds, float speed_m_s, float tolerance,
+                       float* agg_seconds, double* sigma, uint32_t* pred_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CITYSEER_B200_H */
