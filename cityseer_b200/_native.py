@@ -53,6 +53,8 @@ SIGNATURES = {
     ),  # fmt: skip
     "cs_graph_destroy": (None, [C.c_void_p]),
     "cs_graph_configure": (C.c_int, [C.c_void_p, C.c_uint32, C.c_float, C.c_uint32]),
+    "cs_graph_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cs_stage_sources": (C.c_int, [C.c_void_p, C.c_uint64, _u32p, _f32p, _u8p]),
     "cs_centrality_shortest": (
         C.c_int,
         [C.c_void_p, C.c_int, _u32p, _f32p, _u32p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint64, _u32p, _f32p,
@@ -173,6 +175,19 @@ class DeviceGraph:
     def configure(self, reach_capacity: int = 0, delta_seconds: float = 0.0, workers: int = 0) -> None:
         if self._lib.cs_graph_configure(self._h, int(reach_capacity), float(delta_seconds), int(workers)):
             raise ValueError(_err(self._lib))
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        """Run on a caller-owned stream (``torch.cuda.current_stream().cuda_stream``); ``None`` = library stream."""
+        self._lib.cs_graph_set_stream(self._h, C.c_void_p(int(cuda_stream)) if cuda_stream else None)
+
+    def stage_sources(self, sources: np.ndarray, wt: np.ndarray, eligible: np.ndarray | None) -> int:
+        """Upload a source plan; pass ``resident=True`` and the returned count to the next compute call."""
+        sources = np.ascontiguousarray(sources, np.uint32)
+        wt = np.ascontiguousarray(wt, np.float32)
+        ep = None if eligible is None else _ptr(np.ascontiguousarray(eligible, np.uint8), _u8p)
+        if self._lib.cs_stage_sources(self._h, len(sources), _ptr(sources, _u32p), _ptr(wt, _f32p), ep):
+            raise ValueError(_err(self._lib))
+        return len(sources)
 
     def progress(self) -> int:
         return int(self._lib.cs_progress(self._h))

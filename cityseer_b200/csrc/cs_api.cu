@@ -72,7 +72,7 @@ struct cs_graph {
     uint32_t workers = 0, cfg_workers = 0, cfg_rcap = 0;
     float cfg_delta = 0.f;
     float mean_edge_len = 0.f;
-    cudaStream_t stream = nullptr, side_stream = nullptr;
+    cudaStream_t stream = nullptr, side_stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long* h_progress = nullptr;  // pinned
     std::mutex side_mu;
@@ -328,7 +328,8 @@ extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_ex
     CS_CUDA_NULL(cudaMemset(g->d_counters, 0, CS_NCOUNTERS * sizeof(unsigned long long)));
     CS_CUDA_NULL(cudaMalloc(&g->d_error, sizeof(int)));
     CS_CUDA_NULL(cudaMalloc(&g->d_eligible, n));
-    CS_CUDA_NULL(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    CS_CUDA_NULL(cudaStreamCreateWithFlags(&g->own_stream, cudaStreamNonBlocking));
+    g->stream = g->own_stream;
     CS_CUDA_NULL(cudaStreamCreateWithFlags(&g->side_stream, cudaStreamNonBlocking));
     for (auto& e : g->ev) CS_CUDA_NULL(cudaEventCreate(&e));
     CS_CUDA_NULL(cudaHostAlloc(&g->h_progress, sizeof(unsigned long long), cudaHostAllocDefault));
@@ -348,7 +349,7 @@ extern "C" void cs_graph_destroy(cs_graph* g) {
     if (g->h_progress) cudaFreeHost(g->h_progress);
     for (auto& e : g->ev)
         if (e) cudaEventDestroy(e);
-    if (g->stream) cudaStreamDestroy(g->stream);
+    if (g->own_stream) cudaStreamDestroy(g->own_stream);
     if (g->side_stream) cudaStreamDestroy(g->side_stream);
     delete g;
 }
@@ -359,6 +360,12 @@ extern "C" int cs_graph_configure(cs_graph* g, uint32_t reach_capacity, float de
     if (delta_seconds > 0.f) g->cfg_delta = delta_seconds;
     if (workers) g->cfg_workers = workers;
     if (reach_capacity || workers) g->arena_kind = -1;  // force re-allocation
+    return 0;
+}
+
+extern "C" int cs_graph_set_stream(cs_graph* g, void* cuda_stream) {
+    if (!g) return cs_fail("null graph");
+    g->stream = cuda_stream ? (cudaStream_t)cuda_stream : g->own_stream;
     return 0;
 }
 
@@ -493,6 +500,16 @@ static int stage_sources(cs_graph* g, uint64_t n_sources, const uint32_t* source
     else
         CS_CUDA(cudaMemcpyAsync(g->d_eligible, g->d_live, g->n, cudaMemcpyDeviceToDevice, g->stream));
     g->n_resident_sources = n_sources;
+    return 0;
+}
+
+extern "C" int cs_stage_sources(cs_graph* g, uint64_t n_sources, const uint32_t* sources, const float* source_wt,
+                                const uint8_t* eligible) {
+    if (!g) return cs_fail("null graph");
+    if (!sources || !source_wt) return cs_fail("null source plan");
+    CS_CUDA(cudaSetDevice(g->device));
+    if (stage_sources(g, n_sources, sources, source_wt, eligible)) return 1;
+    CS_CUDA(cudaStreamSynchronize(g->stream));
     return 0;
 }
 

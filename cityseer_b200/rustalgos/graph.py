@@ -646,10 +646,12 @@ class NetworkStructure:
             raise ValueError("source_indices and sampling_weights are mutually exclusive")
         node_indices = f.node_indices
         if source_indices is not None:
-            src = np.asarray(list(source_indices), dtype=np.int64)
-            for s in src.tolist():
-                if s < 0 or s >= nb or not f.node_exists[s]:
-                    raise ValueError(f"node index {s} does not exist in the graph")
+            src = np.asarray(source_indices if isinstance(source_indices, np.ndarray) else list(source_indices), dtype=np.int64)
+            bad = (src < 0) | (src >= nb)
+            if not bad.any():
+                bad = f.node_exists[src] == 0
+            if bad.any():
+                raise ValueError(f"node index {int(src[np.nonzero(bad)[0][0]])} does not exist in the graph")
         live_mask = f.live.astype(bool) & f.node_exists.astype(bool)
         n_live = int(live_mask[node_indices].sum())
         eligible = np.zeros(nb, np.uint8)

@@ -61,6 +61,16 @@ void cs_graph_destroy(cs_graph* g);
  * resident warps.  */
 int cs_graph_configure(cs_graph* g, uint32_t reach_capacity, float delta_seconds, uint32_t workers);
 
+/* Run subsequent calls on a caller-owned CUDA stream (e.g. torch's current stream) so that a collective enqueued by the
+ * caller orders after the kernels; pass NULL to return to the library's own non-blocking stream. */
+int cs_graph_set_stream(cs_graph* g, void* cuda_stream);
+
+/* Stage a source plan in device memory ahead of a compute call; a following compute call that passes sources == NULL
+ * (and the same n_sources) runs on the resident plan with no host-to-device copy (SourceSamplingPlan,
+ * centrality.rs:447-456 — sources, per-source weight, source_eligible). */
+int cs_stage_sources(cs_graph* g, uint64_t n_sources, const uint32_t* sources, const float* source_wt,
+                     const uint8_t* eligible);
+
 /* Replaces NetworkStructure.centrality_shortest (centrality.rs:1624-1874) after threshold pairing and source planning
  * (which stay on the host: common.rs:239-270, centrality.rs:1032-1139).
  *   distances/betas/seconds [D]   paired thresholds
