@@ -130,8 +130,8 @@ extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_ex
         cs_fail("NetworkStructure contains no nodes.");
         return nullptr;
     }
-    if (node_bound >= 0x7fffffffu) {
-        cs_fail("node_bound too large");
+    if (node_bound > CS_NODE_MASK) {
+        cs_fail("node_bound %u exceeds the supported maximum of %u nodes", node_bound, CS_NODE_MASK);
         return nullptr;
     }
     CS_CUDA_NULL(cudaSetDevice(device));
@@ -264,14 +264,17 @@ extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_ex
         ir.nbr = s;
         ir.sec = 0.f;
         ir.aux = twin >= 0 ? length[twin] : 0.f;
-        ir.meta = (out_slot[e] - out_off[s]) | (twin >= 0 ? 0x100u : 0u) | (self_loop ? 0x200u : 0u);
+        // meta[21:16] = 1 + position of the twin (d->s) inside s's in-list: the edge a search item for s skips
+        const uint32_t back = (twin >= 0 && !self_loop) ? (in_slot[twin] - in_off[s] + 1u) : 0u;
+        ir.meta = (out_slot[e] - out_off[s]) | (twin >= 0 ? 0x100u : 0u) | (self_loop ? 0x200u : 0u) | (back << 16);
         in_num[in_slot[e]] = num;
         in_imp[in_slot[e]] = twin >= 0 ? imp_factor[twin] : 1.0f;
         CsEdge& orc = out_rec[out_slot[e]];
         orc.nbr = d;
         orc.sec = 0.f;
-        orc.aux = length[e];
-        orc.meta = (in_slot[e] - in_off[d]) | (canonical[e] ? 0x100u : 0u) | (self_loop ? 0x200u : 0u);
+        orc.aux = twin >= 0 ? length[twin] : 0.f;  // length of the twin d->s (segment: origin / last segment lengths)
+        orc.meta = (in_slot[e] - in_off[d]) | (canonical[e] ? 0x100u : 0u) | (self_loop ? 0x200u : 0u) |
+                   (twin >= 0 ? 0x400u : 0u);
         out_num[out_slot[e]] = num;
         if (!ang_rec.empty()) {
             // angular record: nbr | exit slot at s (bit 30) | entry slot at d (bit 31); sec uses use_impedance = false
@@ -389,11 +392,11 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
         g->d_arena = nullptr;
     }
     const size_t nstates = kind == 2 ? (size_t)g->n * 2 : g->n;
-    uint32_t rcap = g->cfg_rcap ? g->cfg_rcap : (1u << 17);
+    uint32_t rcap = g->cfg_rcap ? g->cfg_rcap : (1u << 16);
     rcap = (uint32_t)std::min<size_t>(rcap, nstates);
     rcap = std::max(rcap, 32u);
-    const uint32_t qcap = rcap * 4 + 64;
-    uint32_t workers = g->cfg_workers ? g->cfg_workers : (uint32_t)g->sm_count * 2 * CS_WARPS_PER_CTA;
+    const uint32_t qcap = rcap * 2 + 64;
+    uint32_t workers = g->cfg_workers ? g->cfg_workers : (uint32_t)g->sm_count * CS_MIN_BLOCKS * CS_WARPS_PER_CTA;
     workers = std::max<uint32_t>(CS_WARPS_PER_CTA, workers / CS_WARPS_PER_CTA * CS_WARPS_PER_CTA);
     CsArenaLayout L{};
     size_t off = 0;
@@ -425,18 +428,9 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
     g->arena_bytes = (size_t)workers * L.stride;
     CS_CUDA(cudaMalloc(&g->d_arena, g->arena_bytes));
     // dense maps start at {inf, none}; each search resets exactly what it touched
-    for (uint32_t wk = 0; wk < workers; ++wk) {
-        // one launch per worker region would be slow; instead initialise all regions with a strided kernel below
-        (void)wk;
-    }
     {
-        // ds regions are not contiguous across workers: launch once per worker block of regions via a 2-D trick —
-        // simplest is a loop of async launches on the compute stream (done once per arena allocation).
-        for (uint32_t wk = 0; wk < workers; ++wk) {
-            uint2* ds = reinterpret_cast<uint2*>(g->d_arena + (size_t)wk * L.stride + L.ds);
-            int blocks = (int)std::min<size_t>((nstates + 255) / 256, 256);
-            cs_k_init_ds<<<blocks, 256, 0, g->stream>>>(ds, nstates);
-        }
+        dim3 grid((unsigned)std::min<size_t>((nstates + 255) / 256, 64), workers);
+        cs_k_init_ds<<<grid, 256, 0, g->stream>>>(g->d_arena, L.stride, L.ds, nstates);
         CS_CUDA(cudaGetLastError());
         CS_CUDA(cudaStreamSynchronize(g->stream));
     }
@@ -637,7 +631,7 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
     p.arena = g->d_arena;
     p.lay = g->lay;
     p.delta = default_delta(g, speed);
-    p.bin_scale = (float)CS_NBINS / ((float)max_sec + 1.0f);
+    p.bin_scale = (float)CS_NBINS / (((float)max_sec + 1.0f) * ((float)max_sec + 1.0f));  // cs_bin is quadratic
     p.dump_agg = dump_agg;
     p.dump_sigma = dump_sigma;
     p.dump_npred = dump_npred;
@@ -645,7 +639,13 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
                                                        (n_sources + CS_WARPS_PER_CTA - 1) / CS_WARPS_PER_CTA);
     CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
     if (grid > 0) {
-        cs_k_shortest<<<grid, CS_WARPS_PER_CTA * 32, 0, g->stream>>>(p);
+        const int threads = CS_WARPS_PER_CTA * 32;
+        if (D == 1) cs_k_shortest<1><<<grid, threads, 0, g->stream>>>(p);
+        else if (D == 2) cs_k_shortest<2><<<grid, threads, 0, g->stream>>>(p);
+        else if (D == 3) cs_k_shortest<3><<<grid, threads, 0, g->stream>>>(p);
+        else if (D == 4) cs_k_shortest<4><<<grid, threads, 0, g->stream>>>(p);
+        else if (D <= 8) cs_k_shortest<8><<<grid, threads, 0, g->stream>>>(p);
+        else cs_k_shortest<CS_MAX_THRESHOLDS><<<grid, threads, 0, g->stream>>>(p);
         launches += 1;
         CS_CUDA(cudaGetLastError());
     }
