@@ -12,6 +12,7 @@ import sys
 import tempfile
 
 rep, kname = sys.argv[1], sys.argv[2]
+sect = os.environ.get("SECTION", kname)  # mangled-name substring selecting the nvdisasm section (template instance)
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(root, "cityseer_b200", "libcityseer_b200.so")
@@ -25,7 +26,7 @@ inside = False
 cur = None
 for ln in dis:
     if ln.startswith("//---") and ".text." in ln:
-        inside = kname in ln
+        inside = sect in ln
         continue
     if not inside:
         continue
