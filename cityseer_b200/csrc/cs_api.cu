@@ -491,7 +491,7 @@ static int stage_sources(cs_graph* g, uint64_t n_sources, const uint32_t* source
     }
     if (eligible)
         CS_CUDA(cudaMemcpyAsync(g->d_eligible, eligible, g->n, cudaMemcpyHostToDevice, g->stream));
-    else
+    else if (source_wt)
         CS_CUDA(cudaMemcpyAsync(g->d_eligible, g->d_live, g->n, cudaMemcpyDeviceToDevice, g->stream));
     g->n_resident_sources = n_sources;
     return 0;

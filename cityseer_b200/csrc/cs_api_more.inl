@@ -1,3 +1,67 @@
+// ------------------------------------------------------------------------------------------------ segment
+extern "C" int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
+                                     float speed_m_s, int compute_closeness, int compute_betweenness, uint64_t n_sources,
+                                     const uint32_t* sources, double* out, int out_on_device, int accumulate, cs_stats* stats) {
+    if (!g) return cs_fail("null graph");
+    if (!out) return cs_fail("null output");
+    if (check_thresholds(D, seconds)) return 1;
+    if (!compute_closeness && !compute_betweenness)
+        return cs_fail("Either or both closeness and betweenness flags is required, but both parameters are False.");
+    if (!(speed_m_s > 0.f) || !std::isfinite(speed_m_s)) return cs_fail("speed_m_s must be finite and positive, got %f", speed_m_s);
+    if (g->twin_missing)
+        return cs_fail("Edge not found: segment_centrality needs the reverse twin of every directed edge (graph.rs:1291)");
+    CS_CUDA(cudaSetDevice(g->device));
+    if (ensure_arena(g, 0, D)) return 1;
+    uint32_t launches = 0;
+    CS_CUDA(cudaEventRecord(g->ev[0], g->stream));
+    if (stage_sources(g, n_sources, sources, nullptr, nullptr)) return 1;
+    if (prep_seconds(g, speed_m_s, false, &launches)) return 1;
+    CS_CUDA(cudaMemsetAsync(g->d_counters, 0, CS_NCOUNTERS * sizeof(unsigned long long), g->stream));
+    CS_CUDA(cudaMemsetAsync(g->d_error, 0, sizeof(int), g->stream));
+    const size_t elems = (size_t)4 * D * g->n;
+    double* d_out = nullptr;
+    if (acquire_out(g, out, out_on_device, accumulate, elems, &d_out)) return 1;
+    CsSegmentParams p{};
+    p.g = graph_dev(g);
+    p.D = D;
+    p.closeness = compute_closeness;
+    p.betweenness = compute_betweenness;
+    uint32_t max_sec = 0;
+    for (int i = 0; i < D; ++i) {
+        p.dist_f[i] = (float)distances[i];
+        p.beta_f[i] = betas[i];
+        max_sec = std::max(max_sec, seconds[i]);
+    }
+    p.max_seconds = (float)max_sec;
+    p.speed = speed_m_s;
+    p.sources = g->d_sources;
+    p.n_sources = n_sources;
+    p.out = d_out;
+    p.counters = g->d_counters;
+    p.error = g->d_error;
+    p.arena = g->d_arena;
+    p.lay = g->lay;
+    p.delta = default_delta(g, speed_m_s);
+    p.bin_scale = (float)CS_NBINS / (((float)max_sec + 1.0f) * ((float)max_sec + 1.0f));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(g->workers / CS_WARPS_PER_CTA,
+                                                       (n_sources + CS_WARPS_PER_CTA - 1) / CS_WARPS_PER_CTA);
+    CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
+    if (grid > 0) {
+        const int threads = CS_WARPS_PER_CTA * 32;
+        if (D == 1) cs_k_segment<1><<<grid, threads, 0, g->stream>>>(p);
+        else if (D == 2) cs_k_segment<2><<<grid, threads, 0, g->stream>>>(p);
+        else if (D == 3) cs_k_segment<3><<<grid, threads, 0, g->stream>>>(p);
+        else if (D == 4) cs_k_segment<4><<<grid, threads, 0, g->stream>>>(p);
+        else if (D <= 8) cs_k_segment<8><<<grid, threads, 0, g->stream>>>(p);
+        else cs_k_segment<CS_MAX_THRESHOLDS><<<grid, threads, 0, g->stream>>>(p);
+        launches += 1;
+        CS_CUDA(cudaGetLastError());
+    }
+    CS_CUDA(cudaEventRecord(g->ev[2], g->stream));
+    return finish_call(g, out, out_on_device, elems, d_out, stats, launches);
+}
+
+// ------------------------------------------------------------------------------------------------ simplest
 extern "C" int cs_centrality_simplest(cs_graph* g, int D, const uint32_t* distances, const uint32_t* seconds, float speed_m_s,
                                       float tolerance, float angular_scaling_unit, float farness_scaling_offset,
                                       int compute_closeness, int compute_betweenness, uint64_t n_sources,
@@ -7,11 +71,4 @@ extern "C" int cs_centrality_simplest(cs_graph* g, int D, const uint32_t* distan
     (void)farness_scaling_offset; (void)compute_closeness; (void)compute_betweenness; (void)n_sources; (void)sources;
     (void)source_wt; (void)eligible; (void)out; (void)out_on_device; (void)accumulate; (void)stats;
     return cs_fail("cs_centrality_simplest: kernel not built yet");
-}
-extern "C" int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
-                                     float speed_m_s, int compute_closeness, int compute_betweenness, uint64_t n_sources,
-                                     const uint32_t* sources, double* out, int out_on_device, int accumulate, cs_stats* stats) {
-    (void)g; (void)D; (void)distances; (void)betas; (void)seconds; (void)speed_m_s; (void)compute_closeness;
-    (void)compute_betweenness; (void)n_sources; (void)sources; (void)out; (void)out_on_device; (void)accumulate; (void)stats;
-    return cs_fail("cs_segment_centrality: kernel not built yet");
 }
