@@ -67,6 +67,7 @@ struct cs_graph {
     uint8_t* d_arena = nullptr;
     size_t arena_bytes = 0;
     CsArenaLayout lay{};
+    CsAngLayout ang_lay{};
     int arena_D = 0;
     int arena_kind = -1;
     uint32_t workers = 0, cfg_workers = 0, cfg_rcap = 0;
@@ -441,6 +442,61 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
     return 0;
 }
 
+// angular arena (two states per node, explicit predecessor lists, lane-0 heap)
+static int ensure_arena_angular(cs_graph* g, int D) {
+    if (g->d_arena && g->arena_kind == 2 && g->arena_D >= D) return 0;
+    if (g->d_arena) {
+        CS_CUDA(cudaFree(g->d_arena));
+        g->d_arena = nullptr;
+    }
+    const size_t nstates = (size_t)g->n * 2;
+    uint32_t rcap = g->cfg_rcap ? g->cfg_rcap : (1u << 16);
+    rcap = (uint32_t)std::min<size_t>(std::max<size_t>(rcap, 64), nstates);
+    const uint32_t hcap = rcap * 4 + 64;
+    uint32_t workers = g->cfg_workers ? g->cfg_workers : (uint32_t)g->sm_count * CS_MIN_BLOCKS * CS_WARPS_PER_CTA;
+    workers = std::max<uint32_t>(CS_WARPS_PER_CTA, workers / CS_WARPS_PER_CTA * CS_WARPS_PER_CTA);
+    CsAngLayout L{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    L.ds = take(nstates * sizeof(uint2));
+    L.dn = take((size_t)g->n * sizeof(uint2));
+    L.st_state = take((size_t)rcap * 4);
+    L.st_secs = take((size_t)rcap * 4);
+    L.st_cost = take((size_t)rcap * 4);
+    L.st_sigma = take((size_t)rcap * 8);
+    L.st_np = take((size_t)rcap * 4);
+    L.st_preds = take((size_t)rcap * 4 * CS_ANG_MAXPRED);
+    L.order = take((size_t)rcap * 4);
+    L.pos = take((size_t)rcap * 4);
+    L.delta = take((size_t)rcap * 8 * D);
+    L.pending = take((size_t)rcap * 4);
+    L.heap = take((size_t)hcap * 8);
+    L.stride = align_up(off, 4096);
+    L.rcap = rcap;
+    L.hcap = hcap;
+    size_t free_b = 0, total_b = 0;
+    CS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = (size_t)((double)free_b * 0.80);
+    while (workers > CS_WARPS_PER_CTA && (size_t)workers * L.stride > budget) workers -= CS_WARPS_PER_CTA;
+    if ((size_t)workers * L.stride > budget)
+        return cs_fail("not enough device memory for the search arena (%zu bytes per worker)", L.stride);
+    g->arena_bytes = (size_t)workers * L.stride;
+    CS_CUDA(cudaMalloc(&g->d_arena, g->arena_bytes));
+    dim3 grid((unsigned)std::min<size_t>((nstates + 255) / 256, 64), workers);
+    cs_k_init_ang<<<grid, 256, 0, g->stream>>>(g->d_arena, L.stride, L.ds, nstates, L.dn, g->n);
+    CS_CUDA(cudaGetLastError());
+    CS_CUDA(cudaStreamSynchronize(g->stream));
+    g->ang_lay = L;
+    g->workers = workers;
+    g->arena_D = D;
+    g->arena_kind = 2;
+    return 0;
+}
+
 __global__ void cs_k_prep_seconds(CsEdge* rec, const float* num, uint64_t E, float speed) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < E) rec[i].sec = __fdiv_rn(num[i], speed);
@@ -553,6 +609,8 @@ static int finish_call(cs_graph* g, double* out, int out_on_device, size_t elems
                        g->lay.rcap);
     if (herr == CS_ERR_QUEUE_OVERFLOW)
         return cs_fail("search queue overflow (capacity %u); raise reach_capacity via cs_graph_configure", g->lay.qcap);
+    if (herr == CS_ERR_PRED_OVERFLOW)
+        return cs_fail("a dual state acquired more than %d tied predecessors (unsupported)", CS_ANG_MAXPRED);
     if (herr) return cs_fail("device error %d", herr);
     return 0;
 }

@@ -67,8 +67,70 @@ extern "C" int cs_centrality_simplest(cs_graph* g, int D, const uint32_t* distan
                                       int compute_closeness, int compute_betweenness, uint64_t n_sources,
                                       const uint32_t* sources, const float* source_wt, const uint8_t* eligible, double* out,
                                       int out_on_device, int accumulate, cs_stats* stats) {
-    (void)g; (void)D; (void)distances; (void)seconds; (void)speed_m_s; (void)tolerance; (void)angular_scaling_unit;
-    (void)farness_scaling_offset; (void)compute_closeness; (void)compute_betweenness; (void)n_sources; (void)sources;
-    (void)source_wt; (void)eligible; (void)out; (void)out_on_device; (void)accumulate; (void)stats;
-    return cs_fail("cs_centrality_simplest: kernel not built yet");
+    (void)distances;
+    if (!g) return cs_fail("null graph");
+    if (!out) return cs_fail("null output");
+    if (!g->is_dual)
+        return cs_fail("centrality_simplest requires a dual graph for angular analysis. Convert the graph with "
+                       "cityseer.tools.graphs.nx_to_dual(...) before ingesting it into NetworkStructure.");
+    if (g->dual_status == 1) return cs_fail("dual edge is missing shared_primal_node_key metadata");
+    if (g->dual_status == 2) return cs_fail("dual node references more than two primal endpoints");
+    if (check_thresholds(D, seconds)) return 1;
+    if (!compute_closeness && !compute_betweenness)
+        return cs_fail("Either or both closeness and betweenness flags is required, but both parameters are False.");
+    if (!(speed_m_s > 0.f) || !std::isfinite(speed_m_s)) return cs_fail("speed_m_s must be finite and positive, got %f", speed_m_s);
+    if (!(tolerance >= CS_TIE_EPS)) return cs_fail("Tolerance must be >= TIE_EPSILON to avoid float-comparison bugs");
+    CS_CUDA(cudaSetDevice(g->device));
+    if (ensure_arena_angular(g, D)) return 1;
+    uint32_t launches = 0;
+    CS_CUDA(cudaEventRecord(g->ev[0], g->stream));
+    if (stage_sources(g, n_sources, sources, source_wt, eligible)) return 1;
+    if (prep_seconds(g, speed_m_s, true, &launches)) return 1;
+    CS_CUDA(cudaMemsetAsync(g->d_counters, 0, CS_NCOUNTERS * sizeof(unsigned long long), g->stream));
+    CS_CUDA(cudaMemsetAsync(g->d_error, 0, sizeof(int), g->stream));
+    const size_t elems = (size_t)4 * D * g->n;
+    double* d_out = nullptr;
+    if (acquire_out(g, out, out_on_device, accumulate, elems, &d_out)) return 1;
+    CsSimplestParams p{};
+    p.n = g->n;
+    p.out_off = g->d_out_off;
+    p.ang_rec = g->d_ang_rec;
+    p.D = D;
+    p.closeness = compute_closeness;
+    p.betweenness = compute_betweenness;
+    p.phase2 = tolerance > CS_TIE_EPS ? 1 : 0;
+    uint32_t max_sec = 0;
+    for (int i = 0; i < D; ++i) {
+        p.sec_f[i] = (float)seconds[i];
+        max_sec = std::max(max_sec, seconds[i]);
+    }
+    p.max_seconds = (float)max_sec;
+    p.tol = tolerance;
+    p.unit = angular_scaling_unit;
+    p.offset = farness_scaling_offset;
+    p.sources = g->d_sources;
+    p.src_wt = g->d_src_wt;
+    p.n_sources = n_sources;
+    p.eligible = g->d_eligible;
+    p.out = d_out;
+    p.counters = g->d_counters;
+    p.error = g->d_error;
+    p.arena = g->d_arena;
+    p.lay = g->ang_lay;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(g->workers / CS_WARPS_PER_CTA,
+                                                       (n_sources + CS_WARPS_PER_CTA - 1) / CS_WARPS_PER_CTA);
+    CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
+    if (grid > 0) {
+        const int threads = CS_WARPS_PER_CTA * 32;
+        if (D == 1) cs_k_simplest<1><<<grid, threads, 0, g->stream>>>(p);
+        else if (D == 2) cs_k_simplest<2><<<grid, threads, 0, g->stream>>>(p);
+        else if (D == 3) cs_k_simplest<3><<<grid, threads, 0, g->stream>>>(p);
+        else if (D == 4) cs_k_simplest<4><<<grid, threads, 0, g->stream>>>(p);
+        else if (D <= 8) cs_k_simplest<8><<<grid, threads, 0, g->stream>>>(p);
+        else cs_k_simplest<CS_MAX_THRESHOLDS><<<grid, threads, 0, g->stream>>>(p);
+        launches += 1;
+        CS_CUDA(cudaGetLastError());
+    }
+    CS_CUDA(cudaEventRecord(g->ev[2], g->stream));
+    return finish_call(g, out, out_on_device, elems, d_out, stats, launches);
 }
