@@ -1,9 +1,10 @@
 """Synthetic street-network generators for the BASELINE.json configs.
 
 Pure numpy (no shapely): a jittered lattice with 10 % of the edges dropped, optionally decomposed into ≈20 m segments
-(config #4) or converted to its dual (config #3).  Every graph goes through ``NetworkStructure.from_arrays`` with the
-same directed-edge insertion order ``io.network_structure_from_nx`` would produce (for each start node, each neighbour),
-so adjacency order, lengths (f64 hypot → f32) and angle sums follow the reference's ingest rules (graph.rs:774, :857).
+(config #4) or converted to its dual (config #3).  Every graph goes through ``NetworkStructure.from_arrays`` with a
+directed-edge insertion order of the same shape ``io.network_structure_from_nx`` produces (for each start node, each of
+its neighbours; both directions of every undirected edge), and lengths (f64 hypot → f32) and angle sums follow the
+reference's ingest rules (graph.rs:774, :857).
 """
 from __future__ import annotations
 
@@ -57,8 +58,8 @@ def decompose(xy: np.ndarray, edges: np.ndarray, max_len: float = 20.0):
 
 
 def _directed_in_ingest_order(n: int, edges: np.ndarray):
-    """Directed edge list in the order io.network_structure_from_nx inserts it: for start node 0..n-1, neighbours in
-    the order networkx discovers them (edge-list order as seen from that node)."""
+    """Directed edge list grouped by start node 0..n-1 (the loop shape of io.network_structure_from_nx), neighbours in
+    edge-list order as seen from that node."""
     m = len(edges)
     src = np.concatenate([edges[:, 0], edges[:, 1]])
     dst = np.concatenate([edges[:, 1], edges[:, 0]])

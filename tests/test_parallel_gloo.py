@@ -1,0 +1,75 @@
+"""Multi-rank path on CPU: two gloo ranks shard the sources, each computes its block (with the CPU oracle standing in for
+the device call), one all-reduce sums the partial results — equal to the single-rank result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import helpers as H
+from cityseer_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle
+
+    _g, _n, _e, ns = H.primal_ns()
+    f = ns.frozen()
+    og = oracle.OracleGraph(f)
+    d, b, s = H.pair(distances=[400, 1600])
+    sources, wt, eligible, *_ = ns._prepare_sources(None, None, None, None)
+
+    def compute(src_block, wt_block):
+        out, _ = og.centrality_shortest(d, b, s, H.SPEED, sources=src_block, wt=wt_block, eligible=eligible)
+        return torch.from_numpy(out)
+
+    total = parallel.sharded_sum(compute, sources, wt)
+    lo, hi = parallel.shard_bounds(len(sources), rank, world)
+    q.put((rank, total.numpy(), (lo, hi)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_sum_matches_single_rank(oracle_mod):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    _g, _n, _e, ns = H.primal_ns()
+    d, b, s = H.pair(distances=[400, 1600])
+    ref, _ = oracle_mod.OracleGraph(ns.frozen()).centrality_shortest(d, b, s, H.SPEED)
+    bounds = sorted(x[2] for x in got)
+    assert bounds[0][0] == 0 and bounds[0][1] == bounds[1][0] and bounds[1][1] == 57
+    for _rank, total, _b in got:
+        assert np.array_equal(total[0], ref[0]) and np.array_equal(total[2], ref[2])
+        np.testing.assert_allclose(total, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 1000003):
+        for w in (1, 2, 3, 8):
+            spans = [parallel.shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
