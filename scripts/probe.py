@@ -22,6 +22,7 @@ ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--closeness", type=int, default=1)
 ap.add_argument("--betweenness", type=int, default=1)
 ap.add_argument("--distances", default="500,1000,2000")
+ap.add_argument("--fn", default="shortest", choices=["shortest", "segment", "simplest"])
 a = ap.parse_args()
 t = time.time()
 ns, info = synth.config(a.cfg, a.scale)
@@ -38,8 +39,15 @@ if a.nsrc:
 dist = [int(x) for x in a.distances.split(",")]
 for rep in range(a.reps):
     t = time.time()
-    r = ns.centrality_shortest(distances=dist, compute_closeness=bool(a.closeness), compute_betweenness=bool(a.betweenness),
-                               pbar_disabled=True, **kw)
+    if a.fn == "shortest":
+        r = ns.centrality_shortest(distances=dist, compute_closeness=bool(a.closeness), compute_betweenness=bool(a.betweenness),
+                                   pbar_disabled=True, **kw)
+    elif a.fn == "simplest":
+        r = ns.centrality_simplest(distances=dist, compute_closeness=bool(a.closeness), compute_betweenness=bool(a.betweenness),
+                                   angular_scaling_unit=90, pbar_disabled=True, **kw)
+    else:
+        r = ns.segment_centrality(distances=dist, compute_closeness=bool(a.closeness), compute_betweenness=bool(a.betweenness),
+                                  pbar_disabled=True)
     wall = time.time() - t
     s = r.stats
     print(json.dumps({"rep": rep, "wall_s": round(wall, 3), "kernel_ms": s["kernel_ms"], "total_ms": s["total_ms"],
