@@ -17,6 +17,10 @@ MAX_THRESHOLDS = 16
 
 _lib = None
 _lib_lock = threading.Lock()
+# options applied to every new DeviceGraph (cs_graph_set_option); CITYSEER_B200_KERNEL=1|2 pins the search kernel
+DEFAULT_OPTIONS: dict = {}
+if os.environ.get("CITYSEER_B200_KERNEL"):
+    DEFAULT_OPTIONS["kernel"] = float(os.environ["CITYSEER_B200_KERNEL"])
 
 
 class CsStats(C.Structure):
@@ -32,6 +36,8 @@ class CsStats(C.Structure):
         ("total_ms", C.c_float),
         ("gpu_launches", C.c_uint32),
         ("workers", C.c_uint32),
+        ("phase_cycles", C.c_uint64 * 8),
+        ("fallback_sources", C.c_uint64),
     ]
 
 
@@ -48,11 +54,12 @@ SIGNATURES = {
     "cs_device_count": (C.c_int, []),
     "cs_graph_create": (
         C.c_void_p,
-        [C.c_uint32, _u8p, _u8p, _f32p, _f64p, C.c_uint64, _u8p, _u32p, _u32p, _u32p, _f32p, _f32p, _f32p, _f32p, _i32p,
+        [C.c_uint32, _u8p, _u8p, _f32p, _f64p, _f64p, _f64p, C.c_uint64, _u8p, _u32p, _u32p, _u32p, _f32p, _f32p, _f32p, _f32p, _i32p,
          _u64p, C.c_int, C.c_int],
     ),  # fmt: skip
     "cs_graph_destroy": (None, [C.c_void_p]),
     "cs_graph_configure": (C.c_int, [C.c_void_p, C.c_uint32, C.c_float, C.c_uint32]),
+    "cs_graph_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "cs_graph_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cs_stage_sources": (C.c_int, [C.c_void_p, C.c_uint64, _u32p, _f32p, _u8p]),
     "cs_centrality_shortest": (
@@ -152,7 +159,9 @@ class DeviceGraph:
         f = frozen
         self.node_bound = int(f.node_bound)
         self._h = lib.cs_graph_create(
-            f.node_bound, _ptr(f.node_exists, _u8p), _ptr(f.live, _u8p), _ptr(f.weight, _f32p), _ptr(f.z, _f64p),
+            f.node_bound, _ptr(f.node_exists, _u8p), _ptr(f.live, _u8p), _ptr(f.weight, _f32p),
+            None if getattr(f, "xs", None) is None else _ptr(f.xs, _f64p),
+            None if getattr(f, "ys", None) is None else _ptr(f.ys, _f64p), _ptr(f.z, _f64p),
             f.edge_bound, _ptr(f.edge_exists, _u8p), _ptr(f.src, _u32p), _ptr(f.dst, _u32p), _ptr(f.edge_idx, _u32p),
             _ptr(f.length, _f32p), _ptr(f.angle_sum, _f32p), _ptr(f.imp, _f32p), _ptr(f.seconds, _f32p),
             _ptr(f.shared_key, _i32p), _ptr(f.stamp, _u64p), 1 if f.is_dual else 0, self.device,
@@ -160,6 +169,8 @@ class DeviceGraph:
         if not self._h:
             raise ValueError(_err(lib))
         self._call_lock = threading.Lock()
+        for k, v in DEFAULT_OPTIONS.items():
+            self.set_option(k, v)
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -174,6 +185,11 @@ class DeviceGraph:
 
     def configure(self, reach_capacity: int = 0, delta_seconds: float = 0.0, workers: int = 0) -> None:
         if self._lib.cs_graph_configure(self._h, int(reach_capacity), float(delta_seconds), int(workers)):
+            raise ValueError(_err(self._lib))
+
+    def set_option(self, name: str, value: float) -> None:
+        """Named tunables (``kernel``, ``page_bits``, ``delta_factor``); see include/cityseer_b200.h."""
+        if self._lib.cs_graph_set_option(self._h, name.encode(), float(value)):
             raise ValueError(_err(self._lib))
 
     def set_stream(self, cuda_stream: int | None) -> None:
@@ -206,6 +222,8 @@ class DeviceGraph:
             "total_ms": float(st.total_ms),
             "gpu_launches": int(st.gpu_launches),
             "workers": int(st.workers),
+            "phase_cycles": [int(st.phase_cycles[i]) for i in range(8)],
+            "fallback_sources": int(st.fallback_sources),
         }
 
     def _thresholds(self, d, b, s):

@@ -10,7 +10,10 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "cs_shortest.cuh"
+#include "cs_shortest2.cuh"
 #include "cs_segment.cuh"
 #include "cs_simplest.cuh"
 
@@ -63,6 +66,8 @@ struct cs_graph {
     int* d_error = nullptr;
     double* d_out = nullptr;
     size_t out_cap = 0;
+    double* d_acc = nullptr;  // node-interleaved accumulators [n][cw] + [n][bw] (shortest)
+    size_t acc_cap = 0;
     // arena
     uint8_t* d_arena = nullptr;
     size_t arena_bytes = 0;
@@ -77,6 +82,35 @@ struct cs_graph {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long* h_progress = nullptr;  // pinned
     std::mutex side_mu;
+    // shared-memory kernel (cs_shortest2.cuh): renumbered graph, new-id source plan, capacity plan
+    bool v2_ok = false;
+    uint32_t *d_orig_of_new = nullptr, *d_new_of_orig = nullptr;
+    uint4* d_node2 = nullptr;
+    CsEdge *d_in2 = nullptr, *d_out2 = nullptr;
+    float *d_in2_num = nullptr, *d_out2_num = nullptr;
+    float cached_speed2 = -1.f;
+    uint32_t *d_sources2 = nullptr, *d_sort_keys = nullptr, *d_sort_vals = nullptr, *d_sort_vals2 = nullptr;
+    uint32_t *d_fallback = nullptr, *d_fb_sources = nullptr, *d_probe = nullptr;
+    float *d_src_wt2 = nullptr, *d_fb_wt = nullptr;
+    uint8_t* d_eligible2 = nullptr;
+    void* d_cub_tmp = nullptr;
+    size_t cub_tmp_bytes = 0;
+    uint64_t sources2_cap = 0, n_sources2 = 0;
+    bool sources2_valid = false;
+    uint8_t* d_scratch2 = nullptr;
+    size_t scratch2_bytes = 0;
+    struct {
+        bool valid = false, use = false;
+        float max_seconds = 0.f, speed = 0.f;
+        int D = 0, ctas_per_sm = 0;
+        uint32_t pb = 0, probe_R = 0, probe_pages = 0;
+        uint64_t n_sources = 0;
+        CsV2Smem sm{};
+    } plan;
+    int opt_kernel = 0;  // 0 auto, 1 global-arena kernel only, 2 shared-memory kernel required
+    uint32_t opt_pb = 4;
+    float opt_delta_factor = 6.0f;
+    uint32_t opt_reach_limit = 0;  // test hook: cap the shared-memory reached-node capacity (forces the fallback pass)
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -112,8 +146,15 @@ static int upload(T** dptr, const std::vector<T>& h) {
     return 0;
 }
 
+static int build_v2_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, const double* xs, const double* ys,
+                          const std::vector<uint32_t>& in_off, const std::vector<uint32_t>& out_off,
+                          const std::vector<CsEdge>& in_rec, const std::vector<CsEdge>& out_rec,
+                          const std::vector<float>& in_num, const std::vector<float>& out_num,
+                          const std::vector<float>& weight, const std::vector<uint8_t>& live, uint32_t max_deg);
+
 extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_exists, const uint8_t* live,
-                                     const float* weight, const double* z, uint64_t edge_bound,
+                                     const float* weight, const double* xs, const double* ys, const double* z,
+                                     uint64_t edge_bound,
                                      const uint8_t* edge_exists, const uint32_t* src, const uint32_t* dst,
                                      const uint32_t* edge_idx, const float* length, const float* angle_sum,
                                      const float* imp_factor, const float* seconds, const int32_t* shared_key,
@@ -324,6 +365,7 @@ extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_ex
         rc |= upload(&g->d_ang_rec, ang_rec);
         rc |= upload(&g->d_ang_num, ang_num);
     }
+    if (!rc) rc = build_v2_graph(g, n, node_exists, xs, ys, in_off, out_off, in_rec, out_rec, in_num, out_num, w, lv, max_deg);
     if (rc) {
         delete g;
         return nullptr;
@@ -348,7 +390,11 @@ extern "C" void cs_graph_destroy(cs_graph* g) {
     for (void* p : {(void*)g->d_in_off, (void*)g->d_out_off, (void*)g->d_in_rec, (void*)g->d_out_rec, (void*)g->d_ang_rec,
                     (void*)g->d_in_num, (void*)g->d_out_num, (void*)g->d_ang_num, (void*)g->d_in_imp, (void*)g->d_weight,
                     (void*)g->d_live, (void*)g->d_sources, (void*)g->d_src_wt, (void*)g->d_eligible, (void*)g->d_counters,
-                    (void*)g->d_error, (void*)g->d_out, (void*)g->d_arena})
+                    (void*)g->d_error, (void*)g->d_out, (void*)g->d_arena, (void*)g->d_acc, (void*)g->d_orig_of_new,
+                    (void*)g->d_new_of_orig, (void*)g->d_node2, (void*)g->d_in2, (void*)g->d_out2, (void*)g->d_in2_num,
+                    (void*)g->d_out2_num, (void*)g->d_sources2, (void*)g->d_sort_keys, (void*)g->d_sort_vals,
+                    (void*)g->d_sort_vals2, (void*)g->d_fallback, (void*)g->d_fb_sources, (void*)g->d_probe,
+                    (void*)g->d_src_wt2, (void*)g->d_fb_wt, (void*)g->d_eligible2, g->d_cub_tmp, (void*)g->d_scratch2})
         if (p) cudaFree(p);
     if (g->h_progress) cudaFreeHost(g->h_progress);
     for (auto& e : g->ev)
@@ -364,6 +410,27 @@ extern "C" int cs_graph_configure(cs_graph* g, uint32_t reach_capacity, float de
     if (delta_seconds > 0.f) g->cfg_delta = delta_seconds;
     if (workers) g->cfg_workers = workers;
     if (reach_capacity || workers) g->arena_kind = -1;  // force re-allocation
+    return 0;
+}
+
+extern "C" int cs_graph_set_option(cs_graph* g, const char* name, double value) {
+    if (!g || !name) return cs_fail("null graph or option name");
+    const std::string k(name);
+    if (k == "kernel") {
+        if (value != 0 && value != 1 && value != 2) return cs_fail("option kernel must be 0 (auto), 1 or 2");
+        g->opt_kernel = (int)value;
+    } else if (k == "page_bits") {
+        if (value < 2 || value > 6) return cs_fail("option page_bits must be in [2, 6]");
+        g->opt_pb = (uint32_t)value;
+    } else if (k == "smem_reach_limit") {
+        g->opt_reach_limit = (uint32_t)value;
+    } else if (k == "delta_factor") {
+        if (!(value > 0)) return cs_fail("option delta_factor must be positive");
+        g->opt_delta_factor = (float)value;
+    } else {
+        return cs_fail("unknown option %s", name);
+    }
+    g->plan.valid = false;
     return 0;
 }
 
@@ -540,6 +607,7 @@ static int stage_sources(cs_graph* g, uint64_t n_sources, const uint32_t* source
     }
     for (uint64_t i = 0; i < n_sources; ++i)
         if (sources[i] >= g->n) return cs_fail("node index %u does not exist in the graph", sources[i]);
+    g->sources2_valid = false;
     if (n_sources) {
         CS_CUDA(cudaMemcpyAsync(g->d_sources, sources, n_sources * 4, cudaMemcpyHostToDevice, g->stream));
         if (source_wt)
@@ -563,7 +631,8 @@ extern "C" int cs_stage_sources(cs_graph* g, uint64_t n_sources, const uint32_t*
     return 0;
 }
 
-static int acquire_out(cs_graph* g, double* out, int out_on_device, int accumulate, size_t elems, double** d_out) {
+static int acquire_out(cs_graph* g, double* out, int out_on_device, int accumulate, size_t elems, double** d_out,
+                       bool zero = true) {
     if (out_on_device) {
         *d_out = out;
     } else {
@@ -576,7 +645,7 @@ static int acquire_out(cs_graph* g, double* out, int out_on_device, int accumula
         }
         *d_out = g->d_out;
     }
-    if (!accumulate) CS_CUDA(cudaMemsetAsync(*d_out, 0, elems * sizeof(double), g->stream));
+    if (!accumulate && zero) CS_CUDA(cudaMemsetAsync(*d_out, 0, elems * sizeof(double), g->stream));
     return 0;
 }
 
@@ -599,6 +668,8 @@ static int finish_call(cs_graph* g, double* out, int out_on_device, size_t elems
         stats->sum_ci = h[CS_C_SUM_CI];
         stats->relaxations = h[CS_C_RELAX];
         for (int i = 0; i < CS_MAX_THRESHOLDS; ++i) stats->reach_totals[i] = h[CS_C_REACH0 + i];
+        for (int i = 0; i < 8; ++i) stats->phase_cycles[i] = h[CS_C_PHASE0 + i];
+        stats->fallback_sources = h[CS_C_FALLBACK];
         cudaEventElapsedTime(&stats->kernel_ms, g->ev[1], g->ev[2]);
         cudaEventElapsedTime(&stats->total_ms, g->ev[0], g->ev[3]);
         stats->gpu_launches = launches;
@@ -609,6 +680,9 @@ static int finish_call(cs_graph* g, double* out, int out_on_device, size_t elems
                        g->lay.rcap);
     if (herr == CS_ERR_QUEUE_OVERFLOW)
         return cs_fail("search queue overflow (capacity %u); raise reach_capacity via cs_graph_configure", g->lay.qcap);
+    if (herr == CS_ERR_ZERO_TIE)
+        return cs_fail("zero-length edge between nodes that tie on (seconds, index): settle order undefined; remove "
+                       "zero-length edges (tools.graphs.nx_simple_geoms does) or select the global-arena kernel");
     if (herr == CS_ERR_PRED_OVERFLOW)
         return cs_fail("a dual state acquired more than %d tied predecessors (unsupported)", CS_ANG_MAXPRED);
     if (herr) return cs_fail("device error %d", herr);
@@ -636,8 +710,10 @@ static int check_thresholds(int D, const uint32_t* seconds) {
 
 static float default_delta(const cs_graph* g, float speed) {
     if (g->cfg_delta > 0.f) return g->cfg_delta;
-    return std::max(1e-3f, 6.0f * g->mean_edge_len / speed);
+    return std::max(1e-3f, g->opt_delta_factor * g->mean_edge_len / speed);
 }
+
+#include "cs_api_v2.inl"
 
 // ------------------------------------------------------------------------------------------------ shortest
 static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
@@ -652,16 +728,78 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
     if (!(speed > 0.f) || !std::isfinite(speed)) return cs_fail("speed_m_s must be finite and positive, got %f", speed);
     if (!(tol >= CS_TIE_EPS)) return cs_fail("Tolerance must be >= TIE_EPSILON to avoid float-comparison bugs");
     CS_CUDA(cudaSetDevice(g->device));
-    if (ensure_arena(g, 0, D)) return 1;
     uint32_t launches = 0;
     CS_CUDA(cudaEventRecord(g->ev[0], g->stream));
     if (stage_sources(g, n_sources, sources, source_wt, eligible)) return 1;
-    if (prep_seconds(g, speed, false, &launches)) return 1;
-    CS_CUDA(cudaMemsetAsync(g->d_counters, 0, CS_NCOUNTERS * sizeof(unsigned long long), g->stream));
     CS_CUDA(cudaMemsetAsync(g->d_error, 0, sizeof(int), g->stream));
     const size_t elems = (size_t)7 * D * g->n;
     double* d_out = nullptr;
-    if (acquire_out(g, out, out_on_device, accumulate, elems, &d_out)) return 1;
+    if (acquire_out(g, out, out_on_device, accumulate, elems, &d_out, false)) return 1;
+    const int cw = cs_shortest_cw(D), bw = cs_shortest_bw(D);
+    const size_t acc_elems = (size_t)g->n * (cw + bw);
+    if (g->acc_cap < acc_elems) {
+        if (g->d_acc) cudaFree(g->d_acc);
+        g->d_acc = nullptr;
+        g->acc_cap = 0;
+        CS_CUDA(cudaMalloc(&g->d_acc, acc_elems * sizeof(double)));
+        g->acc_cap = acc_elems;
+    }
+    uint32_t max_sec = 0;
+    for (int i = 0; i < D; ++i) max_sec = std::max(max_sec, seconds[i]);
+
+    // ---- shared-memory kernel (cs_shortest2.cuh) when the graph and the call fit it
+    bool use_v2 = false;
+    CsShortest2Params q{};
+    if (g->opt_kernel != 1 && g->v2_ok && D <= 8 && n_sources > 0) {
+        if (stage_sources_v2(g, n_sources, &launches)) return 1;
+        if (g->cached_speed2 != speed && g->E) {
+            const int blocks = (int)((g->E + 255) / 256);
+            cs_k_prep_seconds<<<blocks, 256, 0, g->stream>>>(g->d_in2, g->d_in2_num, g->E, speed);
+            cs_k_prep_seconds<<<blocks, 256, 0, g->stream>>>(g->d_out2, g->d_out2_num, g->E, speed);
+            launches += 2;
+            g->cached_speed2 = speed;
+        }
+        q.g.n = g->n;
+        q.g.node2 = g->d_node2;
+        q.g.in2 = g->d_in2;
+        q.g.out2 = g->d_out2;
+        q.g.orig_of_new = g->d_orig_of_new;
+        q.D = D;
+        q.closeness = closeness;
+        q.betweenness = betweenness;
+        q.phase2 = tol > CS_TIE_EPS ? 1 : 0;
+        for (int i = 0; i < D; ++i) {
+            q.dist_f[i] = (float)distances[i];
+            q.beta_f[i] = betas[i];
+            q.beta_d[i] = (double)betas[i];
+        }
+        q.max_seconds = (float)max_sec;
+        q.speed = speed;
+        q.tol = tol;
+        q.sources = g->d_sources2;
+        q.src_wt = g->d_src_wt2;
+        q.n_sources = n_sources;
+        q.eligible = g->d_eligible2;
+        q.acc_c = g->d_acc;
+        q.acc_b = g->d_acc + (size_t)g->n * cw;
+        q.cw = cw;
+        q.bw = bw;
+        q.counters = g->d_counters;
+        q.error = g->d_error;
+        q.fallback = g->d_fallback;
+        q.probe_max = g->d_probe;
+        q.delta = default_delta(g, speed);
+        q.dump_agg = dump_agg;
+        q.dump_sigma = dump_sigma;
+        q.dump_npred = dump_npred;
+        if (v2_plan(g, q, n_sources, &launches)) return 1;
+        use_v2 = g->plan.use;
+    }
+    if (g->opt_kernel == 2 && !use_v2)
+        return cs_fail("the shared-memory kernel cannot serve this call (degree > %d, D > 8, or no layout fits)", CS2_MAX_DEG);
+
+    CS_CUDA(cudaMemsetAsync(g->d_counters, 0, CS_NCOUNTERS * sizeof(unsigned long long), g->stream));
+    CS_CUDA(cudaMemsetAsync(g->d_acc, 0, acc_elems * sizeof(double), g->stream));
 
     CsShortestParams p{};
     p.g = graph_dev(g);
@@ -669,12 +807,10 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
     p.closeness = closeness;
     p.betweenness = betweenness;
     p.phase2 = tol > CS_TIE_EPS ? 1 : 0;
-    uint32_t max_sec = 0;
     for (int i = 0; i < D; ++i) {
         p.dist_f[i] = (float)distances[i];
         p.beta_f[i] = betas[i];
         p.beta_d[i] = (double)betas[i];
-        max_sec = std::max(max_sec, seconds[i]);
     }
     p.max_seconds = (float)max_sec;
     p.speed = speed;
@@ -684,19 +820,24 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
     p.n_sources = n_sources;
     p.eligible = g->d_eligible;
     p.out = d_out;
+    p.acc_c = g->d_acc;
+    p.acc_b = g->d_acc + (size_t)g->n * cw;
+    p.cw = cw;
+    p.bw = bw;
     p.counters = g->d_counters;
     p.error = g->d_error;
-    p.arena = g->d_arena;
-    p.lay = g->lay;
     p.delta = default_delta(g, speed);
     p.bin_scale = (float)CS_NBINS / (((float)max_sec + 1.0f) * ((float)max_sec + 1.0f));  // cs_bin is quadratic
     p.dump_agg = dump_agg;
     p.dump_sigma = dump_sigma;
     p.dump_npred = dump_npred;
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(g->workers / CS_WARPS_PER_CTA,
-                                                       (n_sources + CS_WARPS_PER_CTA - 1) / CS_WARPS_PER_CTA);
-    CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
-    if (grid > 0) {
+    auto launch_v1 = [&](uint64_t m) -> int {
+        if (ensure_arena(g, 0, D)) return 1;
+        if (prep_seconds(g, speed, false, &launches)) return 1;
+        p.arena = g->d_arena;
+        p.lay = g->lay;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(g->workers / CS_WARPS_PER_CTA, (m + CS_WARPS_PER_CTA - 1) / CS_WARPS_PER_CTA);
+        if (grid == 0) return 0;
         const int threads = CS_WARPS_PER_CTA * 32;
         if (D == 1) cs_k_shortest<1><<<grid, threads, 0, g->stream>>>(p);
         else if (D == 2) cs_k_shortest<2><<<grid, threads, 0, g->stream>>>(p);
@@ -706,8 +847,53 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
         else cs_k_shortest<CS_MAX_THRESHOLDS><<<grid, threads, 0, g->stream>>>(p);
         launches += 1;
         CS_CUDA(cudaGetLastError());
+        return 0;
+    };
+    const int nblk = (int)((g->n + 255) / 256);
+
+    if (use_v2) {
+        q.sm = g->plan.sm;
+        q.probe = 0;
+        q.bin_scale = (float)q.sm.NB / (((float)max_sec + 1.0f) * ((float)max_sec + 1.0f));
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_sources, (uint64_t)g->sm_count * g->plan.ctas_per_sm);
+        size_t stride = 0;
+        if (v2_scratch(g, q.sm, D, grid, &stride)) return 1;
+        q.scratch = g->d_scratch2;
+        q.scratch_stride = stride;
+        g->workers = grid;
+        CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
+        CS_CUDA(v2_launch(q, grid, g->stream, nullptr));
+        cs_k_epilogue_shortest2<<<nblk, 256, 0, g->stream>>>(q.acc_c, q.acc_b, d_out, g->d_orig_of_new, g->n, D, cw, bw,
+                                                             closeness, betweenness, accumulate);
+        launches += 2;
+        CS_CUDA(cudaGetLastError());
+        // sources that did not fit the shared-memory capacities: global-arena kernel, accumulated on top
+        unsigned long long n_fb = 0;
+        CS_CUDA(cudaMemcpyAsync(&n_fb, g->d_counters + CS_C_FALLBACK, sizeof(n_fb), cudaMemcpyDeviceToHost, g->stream));
+        CS_CUDA(cudaStreamSynchronize(g->stream));
+        if (n_fb > 0) {
+            cs_k_gather_fallback<<<(int)((n_fb + 255) / 256), 256, 0, g->stream>>>(g->d_fallback, n_fb, g->d_sources2, g->d_src_wt2,
+                                                                                  g->d_orig_of_new, g->d_fb_sources, g->d_fb_wt);
+            CS_CUDA(cudaMemsetAsync(g->d_counters + CS_C_NEXT, 0, sizeof(unsigned long long), g->stream));
+            CS_CUDA(cudaMemsetAsync(g->d_acc, 0, acc_elems * sizeof(double), g->stream));
+            p.sources = g->d_fb_sources;
+            p.src_wt = g->d_fb_wt;
+            p.n_sources = n_fb;
+            if (launch_v1(n_fb)) return 1;
+            cs_k_epilogue_shortest<<<nblk, 256, 0, g->stream>>>(p.acc_c, p.acc_b, d_out, g->n, D, cw, bw, closeness, betweenness, 1);
+            launches += 2;
+            CS_CUDA(cudaGetLastError());
+        }
+        CS_CUDA(cudaEventRecord(g->ev[2], g->stream));
+    } else {
+        CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
+        if (launch_v1(n_sources)) return 1;
+        cs_k_epilogue_shortest<<<nblk, 256, 0, g->stream>>>(p.acc_c, p.acc_b, d_out, g->n, D, cw, bw, closeness, betweenness,
+                                                            accumulate);
+        launches += 1;
+        CS_CUDA(cudaGetLastError());
+        CS_CUDA(cudaEventRecord(g->ev[2], g->stream));
     }
-    CS_CUDA(cudaEventRecord(g->ev[2], g->stream));
     return finish_call(g, out, out_on_device, elems, d_out, stats, launches);
 }
 

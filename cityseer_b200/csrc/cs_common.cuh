@@ -37,10 +37,10 @@ struct CsGraphDev {
 };
 
 // Device counters (one block of 8 u64 + reach totals) accumulated with one atomic per source per field.
-enum { CS_C_SOURCES = 0, CS_C_SETTLED, CS_C_EDGE_ITERS, CS_C_SUM_RI, CS_C_SUM_CI, CS_C_RELAX, CS_C_PROGRESS, CS_C_NEXT, CS_C_REACH0 };
+enum { CS_C_SOURCES = 0, CS_C_SETTLED, CS_C_EDGE_ITERS, CS_C_SUM_RI, CS_C_SUM_CI, CS_C_RELAX, CS_C_PROGRESS, CS_C_NEXT, CS_C_FALLBACK, CS_C_PHASE0, CS_C_REACH0 = CS_C_PHASE0 + 8 };
 #define CS_NCOUNTERS (CS_C_REACH0 + CS_MAX_THRESHOLDS)
 
-enum { CS_ERR_NONE = 0, CS_ERR_REACH_OVERFLOW = 1, CS_ERR_QUEUE_OVERFLOW = 2 };
+enum { CS_ERR_NONE = 0, CS_ERR_REACH_OVERFLOW = 1, CS_ERR_QUEUE_OVERFLOW = 2, CS_ERR_PRED_OVERFLOW_ = 3, CS_ERR_ZERO_TIE = 4 };
 
 __device__ __forceinline__ uint32_t cs_lane() { return threadIdx.x & 31u; }
 __device__ __forceinline__ uint32_t cs_lanemask_lt() {

@@ -22,7 +22,10 @@ struct CsShortestParams {
     const float* src_wt;
     unsigned long long n_sources;
     const uint8_t* eligible;
-    double* out;  // [7][D][n]
+    double* out;    // [7][D][n] final layout (written by cs_k_epilogue_shortest)
+    double* acc_c;  // [n][cw] node-interleaved closeness accumulators: slot q = 5 * i + m
+    double* acc_b;  // [n][bw] node-interleaved betweenness accumulators: slot q = i (plain), D + i (beta)
+    int cw, bw;
     unsigned long long* counters;
     int* error;
     uint8_t* arena;
@@ -63,7 +66,6 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
     const CsWarpArena A = cs_arena(p.arena, p.lay, worker);
     const int D = p.D;
     const int D2 = 2 * D;
-    const size_t n = p.g.n;
     const float one_minus = 1.0f - CS_TIE_EPS, one_plus = 1.0f + CS_TIE_EPS;
     const float one_plus_tol = 1.0f + p.tol;
 
@@ -79,7 +81,10 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
         // ------------------------------------------------------------------ P1 + P2
         unsigned long long relax = 0, edge_iters = 0;
         int fail = 0;
+        long long tc[7];
+        tc[0] = clock64();
         const uint32_t R = cs_p1_search(p.g, A, src, p.max_seconds, p.delta, relax, fail);
+        tc[1] = clock64();
         if (fail) {
             if (lane == 0) atomicCAS(p.error, 0, fail);
             break;
@@ -89,6 +94,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
             histE[lane] = 0;
         }
         cs_p2_order(p.g, A, bins, src, R, p.bin_scale, edge_iters);
+        tc[2] = clock64();
 
         // ------------------------------------------------------------------ P3: predecessors + sigma (outgoing edges)
         for (uint32_t b0 = 0; b0 < R; b0 += 32) {
@@ -204,6 +210,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
         }
 
         // ------------------------------------------------------------------ P4: closeness scatter to targets
+        tc[3] = clock64();
         unsigned long long n_ri = 0, n_ci = 0;
         if (p.closeness) {
             if (lane < (uint32_t)D) {
@@ -219,30 +226,66 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
             }
             __syncwarp();
             const float cycles_wt = __fdiv_rn(wt, __ldg(&p.g.weight[src]));  // centrality.rs:1730
-            const double wt_d = (double)wt;
-            const size_t ms = (size_t)D * n;
-            for (uint32_t r = lane; r < R; r += 32) {
-                const uint32_t node = cs_ld(&A.s_node[r]);
-                if (node == src) continue;
-                const float cost = __fmul_rn(cs_ld(&A.s_agg[r]), p.speed);
+            // Packed scatter: the 5*D accumulators of one target are contiguous (one or two 128-byte lines), so a warp
+            // instruction covers 32/LP targets with LP consecutive doubles each instead of 32 unrelated lines
+            // (profiles/r01c_red_microbench.txt: 8-9x the red.f64 throughput of the per-metric [M][D][N] layout).
+            constexpr int NQ = 5 * DT;
+            constexpr int LP = NQ <= 16 ? 16 : 32;
+            constexpr int G = 32 / LP;
+            const uint32_t ql = lane & (LP - 1);
+            const int nq = 5 * D;
+            // lane-constant slot description (single round when 5*DT <= LP, else per round below)
+            for (uint32_t b0 = 0; b0 < R; b0 += 32) {
+                const uint32_t r = b0 + lane;
+                uint32_t node = 0;
+                float cost = __uint_as_float(CS_INF_BITS);
+                if (r < R) {
+                    node = cs_ld(&A.s_node[r]);
+                    if (node != src) cost = __fmul_rn(cs_ld(&A.s_agg[r]), p.speed);
+                }
+                // per-target terms formed once by the target's own lane, exactly as centrality.rs:1755-1777 (f32)
                 const float far_t = __fmul_rn(cost, wt);
                 const float harm_t = __fmul_rn(__fdiv_rn(1.0f, cost), wt);
+                float bet_t[DT];
 #pragma unroll
-                for (int i = 0; i < DT; ++i) {
-                    if (i < D && cost <= p.dist_f[i]) {
-                        double* o = p.out + (size_t)i * n + node;
-                        cs_red_add(o, wt_d);
-                        cs_red_add(o + ms, (double)far_t);
-                        cs_red_add(o + 2 * ms, (double)__fmul_rn(rankf[i], cycles_wt));
-                        cs_red_add(o + 3 * ms, (double)harm_t);
-                        cs_red_add(o + 4 * ms, (double)__fmul_rn(expf(__fmul_rn(-p.beta_f[i], cost)), wt));
-                        ++n_ri;
+                for (int i = 0; i < DT; ++i)
+                    bet_t[i] = (i < D && cost <= p.dist_f[i]) ? __fmul_rn(expf(__fmul_rn(-p.beta_f[i], cost)), wt) : 0.0f;
+                const uint32_t cnt = min(32u, R - b0);
+                for (uint32_t g0 = 0; g0 < cnt; g0 += G) {
+                    const int sl = (int)(g0 + lane / LP);
+                    const float c = __shfl_sync(CS_FULL, cost, sl);
+                    const uint32_t nd = __shfl_sync(CS_FULL, node, sl);
+                    const float f1 = __shfl_sync(CS_FULL, far_t, sl);
+                    const float f3 = __shfl_sync(CS_FULL, harm_t, sl);
+                    float f4[DT];
+#pragma unroll
+                    for (int i = 0; i < DT; ++i) f4[i] = __shfl_sync(CS_FULL, bet_t[i], sl);
+#pragma unroll
+                    for (int q0 = 0; q0 < NQ; q0 += LP) {
+                        const int q = q0 + (int)ql;
+                        if (q < nq) {
+                            const int i = q / 5, m = q - 5 * i;
+                            if (c <= p.dist_f[i]) {
+                                float v = wt;
+                                if (m == 0) ++n_ri;
+                                if (m == 1) v = f1;
+                                if (m == 2) v = __fmul_rn(rankf[i], cycles_wt);
+                                if (m == 3) v = f3;
+                                if (m == 4) {
+#pragma unroll
+                                    for (int ii = 0; ii < DT; ++ii)
+                                        if (ii == i) v = f4[ii];
+                                }
+                                cs_red_add(p.acc_c + (size_t)nd * p.cw + q, (double)v);
+                            }
+                        }
                     }
                 }
             }
         }
 
         // ------------------------------------------------------------------ P5: dependencies, reverse settle order
+        tc[4] = clock64();
         if (p.betweenness) {
             const double wt_d = (double)wt;
             for (int b0 = (int)((R - 1) & ~31u); b0 >= 0; b0 -= 32) {
@@ -273,6 +316,9 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
                     }
                 }
                 bool pending = valid;
+                double cr[2 * DT];  // positive credits of this lane's node, slot 2 * i (plain) / 2 * i + 1 (beta-weighted)
+#pragma unroll
+                for (int q = 0; q < 2 * DT; ++q) cr[q] = 0.0;
                 for (;;) {
                     if (pending) {
                         bool ok = true;
@@ -311,8 +357,8 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
                                         const double credit = dpn - seed, creditb = dpb - seedb;
                                         if (credit > 0.0 || creditb > 0.0) {
                                             ++n_ci;
-                                            if (credit > 0.0) cs_red_add(p.out + ((size_t)(5 * D + i)) * n + w, credit * wt_d);
-                                            if (creditb > 0.0) cs_red_add(p.out + ((size_t)(6 * D + i)) * n + w, creditb * wt_d);
+                                            if (credit > 0.0) cr[2 * i] = credit * wt_d;
+                                            if (creditb > 0.0) cr[2 * i + 1] = creditb * wt_d;
                                         }
                                     }
                                 }
@@ -324,11 +370,32 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
                     __syncwarp();
                     if (!__any_sync(CS_FULL, pending)) break;
                 }
+                // packed credit scatter: 32/LPB nodes per warp instruction, LPB consecutive doubles each
+                {
+                    constexpr int NQB = 2 * DT;
+                    constexpr int LPB = NQB <= 2 ? 2 : NQB <= 4 ? 4 : NQB <= 8 ? 8 : NQB <= 16 ? 16 : 32;
+                    constexpr int GB = 32 / LPB;
+                    const int q = (int)(lane & (LPB - 1));
+                    const uint32_t cnt = min(32u, R - (uint32_t)b0);
+                    for (uint32_t g0 = 0; g0 < cnt; g0 += GB) {
+                        const int sl = (int)(g0 + lane / LPB);
+                        const uint32_t nd = __shfl_sync(CS_FULL, w, sl);
+                        double v = 0.0;
+#pragma unroll
+                        for (int qq = 0; qq < NQB; ++qq) {
+                            const double t = __shfl_sync(CS_FULL, cr[qq], sl);
+                            if (q == qq) v = t;
+                        }
+                        if (v > 0.0) cs_red_add(p.acc_b + (size_t)nd * p.bw + q, v);
+                    }
+                }
             }
         }
 
         // ------------------------------------------------------------------ P6: reset the dense map
+        tc[5] = clock64();
         cs_p6_reset(A, R);
+        tc[6] = clock64();
 
         edge_iters = cs_warp_sum(edge_iters);
         relax = cs_warp_sum(relax);
@@ -342,6 +409,49 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
             if (n_ri) atomicAdd(&p.counters[CS_C_SUM_RI], n_ri);
             if (n_ci) atomicAdd(&p.counters[CS_C_SUM_CI], n_ci);
             atomicAdd(&p.counters[CS_C_PROGRESS], 1ull);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) atomicAdd(&p.counters[CS_C_PHASE0 + k], (unsigned long long)(tc[k + 1] - tc[k]));
         }
+    }
+}
+
+// Row widths (in doubles) of the node-interleaved accumulators for the kernel instantiation that serves D thresholds.
+static inline int cs_shortest_dt(int D) { return D <= 4 ? D : D <= 8 ? 8 : CS_MAX_THRESHOLDS; }
+static inline int cs_shortest_cw(int D) {
+    const int nq = 5 * cs_shortest_dt(D);
+    return nq <= 16 ? 16 : (nq + 31) / 32 * 32;
+}
+static inline int cs_shortest_bw(int D) {
+    const int nq = 2 * cs_shortest_dt(D);
+    return nq <= 2 ? 2 : nq <= 4 ? 4 : nq <= 8 ? 8 : nq <= 16 ? 16 : 32;
+}
+
+// Epilogue: node-interleaved accumulators -> the reference's [7][D][node_bound] layout (density, farness, cycles,
+// harmonic, beta, betweenness, betweenness_beta; centrality.rs:152-215).  `add` != 0 accumulates into `out`.
+__global__ void cs_k_epilogue_shortest(const double* __restrict__ acc_c, const double* __restrict__ acc_b, double* out,
+                                       uint32_t n, int D, int cw, int bw, int closeness, int betweenness, int add) {
+    const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= n) return;
+    if (closeness) {
+        const double* row = acc_c + (size_t)node * cw;
+        for (int i = 0; i < D; ++i)
+            for (int m = 0; m < 5; ++m) {
+                double* o = out + ((size_t)(m * D + i)) * n + node;
+                const double v = row[5 * i + m];
+                *o = add ? *o + v : v;
+            }
+    } else if (!add) {
+        for (int q = 0; q < 5 * D; ++q) out[(size_t)q * n + node] = 0.0;
+    }
+    if (betweenness) {
+        const double* row = acc_b + (size_t)node * bw;
+        for (int i = 0; i < D; ++i)
+            for (int b = 0; b < 2; ++b) {
+                double* o = out + ((size_t)((5 + b) * D + i)) * n + node;
+                const double v = row[2 * i + b];
+                *o = add ? *o + v : v;
+            }
+    } else if (!add) {
+        for (int q = 5 * D; q < 7 * D; ++q) out[(size_t)q * n + node] = 0.0;
     }
 }

@@ -178,6 +178,7 @@ class FrozenGraph:
     __slots__ = (
         "node_bound", "node_exists", "live", "weight", "z", "edge_bound", "edge_exists", "src", "dst", "edge_idx",
         "length", "angle_sum", "imp", "seconds", "shared_key", "stamp", "is_dual", "node_indices", "key_names",
+        "xs", "ys",
     )  # fmt: skip
 
 
@@ -514,6 +515,8 @@ class NetworkStructure:
         shared_key=None,
         is_dual: bool = False,
         node_keys=None,
+        x=None,
+        y=None,
     ) -> "NetworkStructure":
         """Array ingest: the same container state as ``add_street_node`` × N then ``add_street_edge`` × E called in
         array order (directed edges; pass both directions), with ``length`` / ``angle_sum`` already measured.
@@ -527,6 +530,10 @@ class NetworkStructure:
         f.live = np.ascontiguousarray(live, dtype=np.uint8)
         f.weight = np.ascontiguousarray(weight, dtype=np.float32)
         f.z = np.full(n, np.nan, dtype=np.float64) if z is None else np.ascontiguousarray(z, dtype=np.float64)
+        f.xs = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+        f.ys = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
+        if (f.xs is None) != (f.ys is None) or (f.xs is not None and (len(f.xs) != n or len(f.ys) != n)):
+            raise ValueError("x and y must both be given with one value per node")
         f.edge_bound = e
         f.edge_exists = np.ones(e, dtype=np.uint8)
         f.src = np.ascontiguousarray(src, dtype=np.uint32)
@@ -568,10 +575,14 @@ class NetworkStructure:
         f.live = np.zeros(nb, np.uint8)
         f.weight = np.zeros(nb, np.float32)
         f.z = np.full(nb, np.nan, np.float64)
+        f.xs = np.zeros(nb, np.float64)
+        f.ys = np.zeros(nb, np.float64)
         for i in range(nb):
             p = self._nodes[i]
             if p is None:
                 continue
+            f.xs[i] = p.x
+            f.ys[i] = p.y
             f.node_exists[i] = 1
             f.live[i] = 1 if p.live else 0
             f.weight[i] = p.weight

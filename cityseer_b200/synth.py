@@ -80,6 +80,8 @@ def primal_network(xy: np.ndarray, edges: np.ndarray, live: np.ndarray | None = 
         dst=dst,
         edge_idx=np.zeros(len(src), np.uint32),
         length=length,
+        x=xy[:, 0],
+        y=xy[:, 1],
     )
 
 
@@ -133,6 +135,8 @@ def dual_network(xy: np.ndarray, edges: np.ndarray) -> NetworkStructure:
         angle_sum=angle,
         shared_key=sh.astype(np.int32),
         is_dual=True,
+        x=mid[:, 0],
+        y=mid[:, 1],
     )
 
 

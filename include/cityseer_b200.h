@@ -36,7 +36,10 @@ typedef struct cs_stats {
     float kernel_ms;          /* CUDA-event time of the search/accumulate kernel on the launching stream */
     float total_ms;           /* CUDA-event time incl. uploads of per-call arrays, zeroing and result download */
     uint32_t gpu_launches;    /* kernels launched by this call */
-    uint32_t workers;         /* resident warps (one source per warp at a time) */
+    uint32_t workers;         /* resident workers (warps or CTAs, one source each at a time) */
+    uint64_t phase_cycles[8]; /* SM clock cycles summed over workers per kernel phase (search, order, predecessors,
+                                 closeness, dependencies, reset, 2 spare): where the kernel's time goes */
+    uint64_t fallback_sources; /* sources the shared-memory kernel handed to the global-arena kernel (capacity overflow) */
 } cs_stats;
 
 const char* cs_last_error(void);
@@ -45,13 +48,15 @@ int cs_device_count(void);
 /* Replaces NetworkStructure construction + add_street_node / add_street_edge ingest (graph.rs:427-452, :728-889) and
  * validate() (:1035-1058): takes the container's payload fields as flat arrays, builds both CSR orientations with
  * 16-byte edge records in petgraph adjacency order (newest edge first), uploads once to `device`.
- *   node arrays [node_bound]: exists, live, weight, z (NaN = no elevation)
+ *   node arrays [node_bound]: exists, live, weight, xs / ys (coordinates; may both be NULL), z (NaN = no elevation).
+ *                             The coordinates only order the device copy of the graph along a Hilbert curve so that
+ *                             the nodes one source reaches are contiguous in memory; results do not depend on them.
  *   edge arrays [edge_bound]: exists, src, dst, edge_idx (payload key), length, angle_sum, imp_factor,
  *                             seconds (NaN for street edges), shared_key (dual: id of shared_primal_node_key, else -1),
  *                             stamp (insertion sequence; larger = newer)
  */
 cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_exists, const uint8_t* live, const float* weight,
-                          const double* z, uint64_t edge_bound, const uint8_t* edge_exists, const uint32_t* src,
+                          const double* xs, const double* ys, const double* z, uint64_t edge_bound, const uint8_t* edge_exists, const uint32_t* src,
                           const uint32_t* dst, const uint32_t* edge_idx, const float* length, const float* angle_sum,
                           const float* imp_factor, const float* seconds, const int32_t* shared_key,
                           const uint64_t* stamp, int is_dual, int device);
@@ -60,6 +65,11 @@ void cs_graph_destroy(cs_graph* g);
 /* Tunables (0 = keep default): arena capacity in reached nodes per source, near/far bucket width in seconds,
  * resident warps.  */
 int cs_graph_configure(cs_graph* g, uint32_t reach_capacity, float delta_seconds, uint32_t workers);
+
+/* Named tunables of the search kernels: "kernel" (0 = choose per call, 1 = global-arena kernel only, 2 = require the
+ * shared-memory kernel), "page_bits" (log2 nodes per shared-memory page, default 4), "delta_factor" (near/far bucket
+ * width in mean edge traversal times, default 6). */
+int cs_graph_set_option(cs_graph* g, const char* name, double value);
 
 /* Run subsequent calls on a caller-owned CUDA stream (e.g. torch's current stream) so that a collective enqueued by the
  * caller orders after the kernels; pass NULL to return to the library's own non-blocking stream. */

@@ -53,4 +53,7 @@ for rep in range(a.reps):
     print(json.dumps({"rep": rep, "wall_s": round(wall, 3), "kernel_ms": s["kernel_ms"], "total_ms": s["total_ms"],
                       "sources": s["sources"], "src_per_s_kernel": s["sources"] / (s["kernel_ms"] / 1e3),
                       "gteps": s["edge_iters"] / (s["kernel_ms"] / 1e3) / 1e9, "R": s["settled"] / max(1, s["sources"]),
-                      "relax_per_settled": s["relaxations"] / max(1, s["settled"]), "workers": s["workers"]}), flush=True)
+                      "relax_per_settled": s["relaxations"] / max(1, s["settled"]), "workers": s["workers"],
+                      "fallback": s["fallback_sources"],
+                      "phase_pct": [round(100.0 * c / max(1, sum(s["phase_cycles"])), 1) for c in s["phase_cycles"]],
+                      "cycles_per_source": sum(s["phase_cycles"]) / max(1, s["sources"])}), flush=True)

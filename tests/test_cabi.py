@@ -37,8 +37,8 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_stats_struct_layout_matches_header():
-    # cs_stats: 6 x u64 + 16 x u64 + 2 x f32 + 2 x u32
-    assert ctypes.sizeof(_native.CsStats) == 6 * 8 + 16 * 8 + 2 * 4 + 2 * 4
+    # cs_stats: 6 x u64 + 16 x u64 + 2 x f32 + 2 x u32 + 8 x u64 (phase cycles) + u64 (fallback sources)
+    assert ctypes.sizeof(_native.CsStats) == 6 * 8 + 16 * 8 + 2 * 4 + 2 * 4 + 8 * 8 + 8
     text = open(os.path.join(ROOT, "include", "cityseer_b200.h")).read()
     assert "#define CS_MAX_THRESHOLDS 16" in text and _native.MAX_THRESHOLDS == 16
 
@@ -56,7 +56,8 @@ def test_no_cpu_fallback(lib):
     f = ns.frozen()
     h = lib.cs_graph_create(
         f.node_bound, f.node_exists.ctypes.data_as(_native._u8p), f.live.ctypes.data_as(_native._u8p),
-        f.weight.ctypes.data_as(_native._f32p), f.z.ctypes.data_as(_native._f64p), f.edge_bound,
+        f.weight.ctypes.data_as(_native._f32p), f.xs.ctypes.data_as(_native._f64p), f.ys.ctypes.data_as(_native._f64p),
+        f.z.ctypes.data_as(_native._f64p), f.edge_bound,
         f.edge_exists.ctypes.data_as(_native._u8p), f.src.ctypes.data_as(_native._u32p), f.dst.ctypes.data_as(_native._u32p),
         f.edge_idx.ctypes.data_as(_native._u32p), f.length.ctypes.data_as(_native._f32p),
         f.angle_sum.ctypes.data_as(_native._f32p), f.imp.ctypes.data_as(_native._f32p),

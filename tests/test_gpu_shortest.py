@@ -14,6 +14,17 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # stated tolerance for floating-point metrics
 
 
+@pytest.fixture(autouse=True, params=[2, 1], ids=["smem-kernel", "arena-kernel"])
+def kernel_choice(request):
+    """Every test runs against both search kernels: 2 = shared-memory CTA-per-source kernel (required, no silent
+    fallback), 1 = global-arena warp-per-source kernel."""
+    from cityseer_b200 import _native
+
+    _native.DEFAULT_OPTIONS["kernel"] = float(request.param)
+    yield request.param
+    _native.DEFAULT_OPTIONS.pop("kernel", None)
+
+
 def check(got, ref, names=("density", "farness", "cycles", "harmonic", "beta", "betweenness", "betweenness_beta")):
     assert got.shape == ref.shape
     assert np.array_equal(got[0], ref[0]), "node_density not bit-exact"
@@ -201,3 +212,16 @@ def test_linearity_property_full_size_graph():
     assert np.array_equal(a._out[0] + b._out[0], full._out[0])
     assert np.array_equal(a._out[2] + b._out[2], full._out[2])
     np.testing.assert_allclose(a._out[1] + b._out[1], full._out[1], rtol=1e-9)
+
+
+def test_smem_kernel_overflow_falls_back_to_arena_kernel(oracle_mod, kernel_choice):
+    # sources whose reach exceeds the shared-memory capacity are re-run by the global-arena kernel and added on top
+    if kernel_choice != 2:
+        pytest.skip("shared-memory kernel only")
+    ns, _ = synth.config("cfg2", 0.2)
+    dev = ns.device_graph()
+    dev.set_option("smem_reach_limit", 256)
+    res, ref, cnt = run_both(oracle_mod, ns, [500, 1000, 2000])
+    check(res._out, ref)
+    assert 0 < res.stats["fallback_sources"] < res.stats["sources"]
+    assert res.stats["settled"] == cnt["settled"] and res.stats["sum_ci"] == cnt["sum_ci"]
