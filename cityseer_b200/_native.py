@@ -12,7 +12,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcityseer_b200.so")
+LIB_PATH = os.environ.get("CITYSEER_B200_LIB") or os.path.join(_HERE, "libcityseer_b200.so")  # env: A/B builds of the same ABI
 MAX_THRESHOLDS = 16
 
 _lib = None
@@ -38,6 +38,10 @@ class CsStats(C.Structure):
         ("workers", C.c_uint32),
         ("phase_cycles", C.c_uint64 * 8),
         ("fallback_sources", C.c_uint64),
+        ("smem_bytes", C.c_uint32),
+        ("ctas_per_sm", C.c_uint32),
+        ("reach_capacity", C.c_uint32),
+        ("slot_capacity", C.c_uint32),
     ]
 
 
@@ -218,12 +222,18 @@ class DeviceGraph:
             "sum_ci": int(st.sum_ci),
             "relaxations": int(st.relaxations),
             "reach_totals": [int(st.reach_totals[i]) for i in range(D)],
+            "dbg15": int(st.reach_totals[15]),
+            "dbg": [int(st.reach_totals[i]) for i in range(10, 15)],
             "kernel_ms": float(st.kernel_ms),
             "total_ms": float(st.total_ms),
             "gpu_launches": int(st.gpu_launches),
             "workers": int(st.workers),
             "phase_cycles": [int(st.phase_cycles[i]) for i in range(8)],
             "fallback_sources": int(st.fallback_sources),
+            "smem_bytes": int(st.smem_bytes),
+            "ctas_per_sm": int(st.ctas_per_sm),
+            "reach_capacity": int(st.reach_capacity),
+            "slot_capacity": int(st.slot_capacity),
         }
 
     def _thresholds(self, d, b, s):

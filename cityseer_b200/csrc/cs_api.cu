@@ -90,8 +90,8 @@ struct cs_graph {
     float *d_in2_num = nullptr, *d_out2_num = nullptr;
     float cached_speed2 = -1.f;
     uint32_t *d_sources2 = nullptr, *d_sort_keys = nullptr, *d_sort_vals = nullptr, *d_sort_vals2 = nullptr;
-    uint32_t *d_fallback = nullptr, *d_fb_sources = nullptr, *d_probe = nullptr;
-    float *d_src_wt2 = nullptr, *d_fb_wt = nullptr;
+    uint32_t *d_fallback = nullptr, *d_fb_sources = nullptr, *d_fb2_sources = nullptr, *d_probe = nullptr;
+    float *d_src_wt2 = nullptr, *d_fb_wt = nullptr, *d_fb2_wt = nullptr;
     uint8_t* d_eligible2 = nullptr;
     void* d_cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
@@ -102,15 +102,20 @@ struct cs_graph {
     struct {
         bool valid = false, use = false;
         float max_seconds = 0.f, speed = 0.f;
-        int D = 0, ctas_per_sm = 0;
+        int D = 0, ctas_per_sm = 0, T = 256;
         uint32_t pb = 0, probe_R = 0, probe_pages = 0;
         uint64_t n_sources = 0;
-        CsV2Smem sm{};
+        CsV2Smem sm{}, sm_big{};
     } plan;
     int opt_kernel = 0;  // 0 auto, 1 global-arena kernel only, 2 shared-memory kernel required
-    uint32_t opt_pb = 4;
-    float opt_delta_factor = 6.0f;
-    uint32_t opt_reach_limit = 0;  // test hook: cap the shared-memory reached-node capacity (forces the fallback pass)
+    uint32_t opt_pb = 3;
+    float opt_delta_factor = 12.0f;
+    float opt_headroom = 1.1f;  // capacity of the primary shared-memory layout relative to the probed maxima
+    int opt_threads = 0;        // 0 = by reach, else 128 or 256 threads per CTA
+    uint64_t last_fallback = 0;
+    bool last_v2 = false;
+    uint32_t opt_reach_limit = 0, opt_reach_limit2 = 0;  // test hooks: cap the reached-node capacity of the primary /
+                                                         // largest shared-memory layout (forces the fallback passes)
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -394,7 +399,8 @@ extern "C" void cs_graph_destroy(cs_graph* g) {
                     (void*)g->d_new_of_orig, (void*)g->d_node2, (void*)g->d_in2, (void*)g->d_out2, (void*)g->d_in2_num,
                     (void*)g->d_out2_num, (void*)g->d_sources2, (void*)g->d_sort_keys, (void*)g->d_sort_vals,
                     (void*)g->d_sort_vals2, (void*)g->d_fallback, (void*)g->d_fb_sources, (void*)g->d_probe,
-                    (void*)g->d_src_wt2, (void*)g->d_fb_wt, (void*)g->d_eligible2, g->d_cub_tmp, (void*)g->d_scratch2})
+                    (void*)g->d_src_wt2, (void*)g->d_fb_wt, (void*)g->d_eligible2, g->d_cub_tmp, (void*)g->d_scratch2,
+                    (void*)g->d_fb2_sources, (void*)g->d_fb2_wt})
         if (p) cudaFree(p);
     if (g->h_progress) cudaFreeHost(g->h_progress);
     for (auto& e : g->ev)
@@ -424,6 +430,14 @@ extern "C" int cs_graph_set_option(cs_graph* g, const char* name, double value) 
         g->opt_pb = (uint32_t)value;
     } else if (k == "smem_reach_limit") {
         g->opt_reach_limit = (uint32_t)value;
+    } else if (k == "smem_reach_limit2") {
+        g->opt_reach_limit2 = (uint32_t)value;
+    } else if (k == "headroom") {
+        if (!(value >= 1.0)) return cs_fail("option headroom must be >= 1");
+        g->opt_headroom = (float)value;
+    } else if (k == "threads") {
+        if (value != 0 && value != 128 && value != 256 && value != 512) return cs_fail("option threads must be 0, 128, 256 or 512");
+        g->opt_threads = (int)value;
     } else if (k == "delta_factor") {
         if (!(value > 0)) return cs_fail("option delta_factor must be positive");
         g->opt_delta_factor = (float)value;
@@ -669,7 +683,11 @@ static int finish_call(cs_graph* g, double* out, int out_on_device, size_t elems
         stats->relaxations = h[CS_C_RELAX];
         for (int i = 0; i < CS_MAX_THRESHOLDS; ++i) stats->reach_totals[i] = h[CS_C_REACH0 + i];
         for (int i = 0; i < 8; ++i) stats->phase_cycles[i] = h[CS_C_PHASE0 + i];
-        stats->fallback_sources = h[CS_C_FALLBACK];
+        stats->fallback_sources = g->last_v2 ? g->last_fallback : 0;
+        stats->smem_bytes = g->last_v2 ? g->plan.sm.total : 0;
+        stats->ctas_per_sm = g->last_v2 ? (uint32_t)g->plan.ctas_per_sm : 0;
+        stats->reach_capacity = g->last_v2 ? g->plan.sm.rcap : 0;
+        stats->slot_capacity = g->last_v2 ? g->plan.sm.S : 0;
         cudaEventElapsedTime(&stats->kernel_ms, g->ev[1], g->ev[2]);
         cudaEventElapsedTime(&stats->total_ms, g->ev[0], g->ev[3]);
         stats->gpu_launches = launches;
@@ -851,33 +869,60 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
     };
     const int nblk = (int)((g->n + 255) / 256);
 
+    g->last_v2 = use_v2;
+    g->last_fallback = 0;
     if (use_v2) {
         q.sm = g->plan.sm;
         q.probe = 0;
         q.bin_scale = (float)q.sm.NB / (((float)max_sec + 1.0f) * ((float)max_sec + 1.0f));
         const uint32_t grid = (uint32_t)std::min<uint64_t>(n_sources, (uint64_t)g->sm_count * g->plan.ctas_per_sm);
-        size_t stride = 0;
+        const uint32_t grid_big = (uint32_t)g->sm_count;
+        size_t stride = 0, stride_big = 0;
+        if (v2_scratch(g, g->plan.sm_big, D, grid_big, &stride_big)) return 1;
         if (v2_scratch(g, q.sm, D, grid, &stride)) return 1;
         q.scratch = g->d_scratch2;
         q.scratch_stride = stride;
         g->workers = grid;
         CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
-        CS_CUDA(v2_launch(q, grid, g->stream, nullptr));
-        cs_k_epilogue_shortest2<<<nblk, 256, 0, g->stream>>>(q.acc_c, q.acc_b, d_out, g->d_orig_of_new, g->n, D, cw, bw,
-                                                             closeness, betweenness, accumulate);
-        launches += 2;
-        CS_CUDA(cudaGetLastError());
-        // sources that did not fit the shared-memory capacities: global-arena kernel, accumulated on top
+        CS_CUDA(v2_launch(q, g->plan.T, grid, g->stream, nullptr));
+        launches += 1;
+        // sources that did not fit the primary layout: once more at the largest layout, then the global-arena kernel
         unsigned long long n_fb = 0;
         CS_CUDA(cudaMemcpyAsync(&n_fb, g->d_counters + CS_C_FALLBACK, sizeof(n_fb), cudaMemcpyDeviceToHost, g->stream));
         CS_CUDA(cudaStreamSynchronize(g->stream));
-        if (n_fb > 0) {
+        g->last_fallback = n_fb;
+        if (n_fb > 0 && g->plan.sm_big.total > q.sm.total) {
+            cs_k_gather_fallback_new<<<(int)((n_fb + 255) / 256), 256, 0, g->stream>>>(g->d_fallback, n_fb, g->d_sources2,
+                                                                                      g->d_src_wt2, g->d_fb_sources, g->d_fb_wt);
+            CS_CUDA(cudaMemsetAsync(g->d_counters + CS_C_NEXT, 0, sizeof(unsigned long long), g->stream));
+            CS_CUDA(cudaMemsetAsync(g->d_counters + CS_C_FALLBACK, 0, sizeof(unsigned long long), g->stream));
+            CsShortest2Params q2 = q;
+            q2.sm = g->plan.sm_big;
+            q2.bin_scale = (float)q2.sm.NB / (((float)max_sec + 1.0f) * ((float)max_sec + 1.0f));
+            q2.sources = g->d_fb_sources;
+            q2.src_wt = g->d_fb_wt;
+            q2.n_sources = n_fb;
+            q2.scratch_stride = stride_big;
+            CS_CUDA(v2_launch(q2, 256, (uint32_t)std::min<uint64_t>(n_fb, grid_big), g->stream, nullptr));
+            launches += 2;
+            CS_CUDA(cudaMemcpyAsync(&n_fb, g->d_counters + CS_C_FALLBACK, sizeof(n_fb), cudaMemcpyDeviceToHost, g->stream));
+            CS_CUDA(cudaStreamSynchronize(g->stream));
+            if (n_fb > 0)
+                cs_k_gather_fallback<<<(int)((n_fb + 255) / 256), 256, 0, g->stream>>>(
+                    g->d_fallback, n_fb, g->d_fb_sources, g->d_fb_wt, g->d_orig_of_new, g->d_fb2_sources, g->d_fb2_wt);
+        } else if (n_fb > 0) {
             cs_k_gather_fallback<<<(int)((n_fb + 255) / 256), 256, 0, g->stream>>>(g->d_fallback, n_fb, g->d_sources2, g->d_src_wt2,
-                                                                                  g->d_orig_of_new, g->d_fb_sources, g->d_fb_wt);
+                                                                                  g->d_orig_of_new, g->d_fb2_sources, g->d_fb2_wt);
+        }
+        cs_k_epilogue_shortest2<<<nblk, 256, 0, g->stream>>>(q.acc_c, q.acc_b, d_out, g->d_orig_of_new, g->n, D, cw, bw,
+                                                             closeness, betweenness, accumulate);
+        launches += 1;
+        CS_CUDA(cudaGetLastError());
+        if (n_fb > 0) {
             CS_CUDA(cudaMemsetAsync(g->d_counters + CS_C_NEXT, 0, sizeof(unsigned long long), g->stream));
             CS_CUDA(cudaMemsetAsync(g->d_acc, 0, acc_elems * sizeof(double), g->stream));
-            p.sources = g->d_fb_sources;
-            p.src_wt = g->d_fb_wt;
+            p.sources = g->d_fb2_sources;
+            p.src_wt = g->d_fb2_wt;
             p.n_sources = n_fb;
             if (launch_v1(n_fb)) return 1;
             cs_k_epilogue_shortest<<<nblk, 256, 0, g->stream>>>(p.acc_c, p.acc_b, d_out, g->n, D, cw, bw, closeness, betweenness, 1);

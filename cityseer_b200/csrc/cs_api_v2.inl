@@ -154,12 +154,23 @@ __global__ void cs_k_gather_fallback(const uint32_t* pos, uint64_t m, const uint
     }
 }
 
+// fallback positions -> new ids and weights (second pass of the shared-memory kernel at its largest layout)
+__global__ void cs_k_gather_fallback_new(const uint32_t* pos, uint64_t m, const uint32_t* sources2, const float* wt2,
+                                         uint32_t* dst, float* dwt) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) {
+        dst[i] = sources2[pos[i]];
+        dwt[i] = wt2[pos[i]];
+    }
+}
+
 // new-id source plan, ascending, from the staged original-index plan (d_sources / d_src_wt / d_eligible)
 static int stage_sources_v2(cs_graph* g, uint64_t m, uint32_t* launches) {
     if (g->sources2_valid && g->n_sources2 == m) return 0;
     if (m > g->sources2_cap) {
         for (void* p : {(void*)g->d_sources2, (void*)g->d_src_wt2, (void*)g->d_sort_keys, (void*)g->d_sort_vals,
-                        (void*)g->d_sort_vals2, (void*)g->d_fallback, (void*)g->d_fb_sources, (void*)g->d_fb_wt})
+                        (void*)g->d_sort_vals2, (void*)g->d_fallback, (void*)g->d_fb_sources, (void*)g->d_fb_wt,
+                        (void*)g->d_fb2_sources, (void*)g->d_fb2_wt})
             if (p) cudaFree(p);
         const size_t b = std::max<uint64_t>(m, 1) * 4;
         CS_CUDA(cudaMalloc(&g->d_sources2, b));
@@ -170,6 +181,8 @@ static int stage_sources_v2(cs_graph* g, uint64_t m, uint32_t* launches) {
         CS_CUDA(cudaMalloc(&g->d_fallback, b));
         CS_CUDA(cudaMalloc(&g->d_fb_sources, b));
         CS_CUDA(cudaMalloc(&g->d_fb_wt, b));
+        CS_CUDA(cudaMalloc(&g->d_fb2_sources, b));
+        CS_CUDA(cudaMalloc(&g->d_fb2_wt, b));
         g->sources2_cap = m;
     }
     if (m) {
@@ -200,7 +213,7 @@ static int stage_sources_v2(cs_graph* g, uint64_t m, uint32_t* launches) {
 }
 
 // ------------------------------------------------------------------------------------------------ layout / launch
-static bool v2_layout(CsV2Smem& M, uint32_t rcap, uint32_t pages, uint32_t pb, int D) {
+static bool v2_layout(CsV2Smem& M, uint32_t rcap, uint32_t pages, uint32_t pb, int D, int T) {
     std::memset(&M, 0, sizeof(M));
     rcap = (uint32_t)align_up(std::max<uint32_t>(rcap, 64), 64);
     uint32_t TB = (uint32_t)std::ceil((double)std::max<uint32_t>(pages, 8) / 0.85);
@@ -212,10 +225,9 @@ static bool v2_layout(CsV2Smem& M, uint32_t rcap, uint32_t pages, uint32_t pb, i
     if (M.S > 65536u || rcap > 65536u) return false;
     M.max_pages = (uint32_t)(TB * 0.92);
     M.rcap = rcap;
-    M.QC = 1024;
-    M.NB = 2048;
-    M.WS = 2048;
-    M.WD = 1024;
+    M.NB = (uint32_t)std::max(512, T);
+    M.WS = 4 * T;  // sigma ring: predecessors up to 2T ranks behind the chunk are read from shared memory
+    M.WD = 2 * T;  // dependency ring: successors up to T ranks beyond the chunk
     const uint32_t ES = 2 * D + 1;
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -228,42 +240,46 @@ static bool v2_layout(CsV2Smem& M, uint32_t rcap, uint32_t pages, uint32_t pb, i
     M.off_defer = take((size_t)M.S / 8);
     M.off_rank = take((size_t)M.S * 2);
     M.off_perm = take((size_t)rcap * 2);
-    M.off_pmask = take(rcap);
-    size_t u = std::max<size_t>((size_t)6 * 4 * M.QC, (size_t)(M.NB + 1) * 4 + (size_t)rcap * 2);
-    u = std::max<size_t>(u, (size_t)M.WS * 8);
-    size_t dep = (size_t)M.WD * (ES * 8 + 4);
-    if (dep > (size_t)M.S * 4 && dep > u) {
-        M.WD = 512;
-        dep = (size_t)M.WD * (ES * 8 + 4);
-    }
+    // union region: P1 two queues of 3 words per item | P2 bins + bin-ordered slots | P3-P5 sigma ring + predecessor masks
+    const size_t u_p2 = align_up((size_t)(M.NB + 1) * 4, 16) + (size_t)rcap * 2;
+    const size_t u_p3 = (size_t)M.WS * 8 + rcap;
+    size_t u = std::max(u_p2, u_p3);
+    M.QC = (uint32_t)std::min<size_t>(1024, std::max<size_t>(u / 24, 64));
+    u = std::max(u, (size_t)M.QC * 24);
+    const size_t dep = (size_t)M.WD * (ES * 8) + 16;
+    M.off_u = take(u);
+    M.off_pmask = M.off_u + M.WS * 8;
     if (dep <= (size_t)M.S * 4) {
-        M.off_u = take(u);
-        M.off_dep = M.off_dist;
+        M.off_dep = M.off_dist;  // distances are dead once the dependencies are accumulated
     } else {
-        u = std::max(u, dep);
-        M.off_u = take(u);
-        M.off_dep = M.off_u;
+        M.off_dep = take(dep);
     }
     M.total = (uint32_t)off;
     return true;
 }
 
-template <int DT>
+template <int DT, int T>
 static cudaError_t v2_launch_t(const CsShortest2Params& p, uint32_t grid, cudaStream_t st, int* occ) {
-    cudaError_t e = cudaFuncSetAttribute(cs_k_shortest2<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.sm.total);
+    cudaError_t e = cudaFuncSetAttribute(cs_k_shortest2<DT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.sm.total);
     if (e != cudaSuccess) return e;
-    if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, cs_k_shortest2<DT>, CS2_T, p.sm.total);
-    cs_k_shortest2<DT><<<grid, CS2_T, p.sm.total, st>>>(p);
+    if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, cs_k_shortest2<DT, T>, T, p.sm.total);
+    cs_k_shortest2<DT, T><<<grid, T, p.sm.total, st>>>(p);
     return cudaGetLastError();
 }
-static cudaError_t v2_launch(const CsShortest2Params& p, uint32_t grid, cudaStream_t st, int* occ) {
+template <int T>
+static cudaError_t v2_launch_d(const CsShortest2Params& p, uint32_t grid, cudaStream_t st, int* occ) {
     switch (cs_shortest_dt(p.D)) {
-        case 1: return v2_launch_t<1>(p, grid, st, occ);
-        case 2: return v2_launch_t<2>(p, grid, st, occ);
-        case 3: return v2_launch_t<3>(p, grid, st, occ);
-        case 4: return v2_launch_t<4>(p, grid, st, occ);
-        default: return v2_launch_t<8>(p, grid, st, occ);
+        case 1: return v2_launch_t<1, T>(p, grid, st, occ);
+        case 2: return v2_launch_t<2, T>(p, grid, st, occ);
+        case 3: return v2_launch_t<3, T>(p, grid, st, occ);
+        case 4: return v2_launch_t<4, T>(p, grid, st, occ);
+        default: return v2_launch_t<8, T>(p, grid, st, occ);
     }
+}
+static cudaError_t v2_launch(const CsShortest2Params& p, int T, uint32_t grid, cudaStream_t st, int* occ) {
+    if (T == 128) return v2_launch_d<128>(p, grid, st, occ);
+    if (T == 256) return v2_launch_d<256>(p, grid, st, occ);
+    return v2_launch_d<512>(p, grid, st, occ);
 }
 
 static const size_t CS2_SMEM_MAX = 227 * 1024 - 2048;  // opt-in limit per CTA minus static shared memory
@@ -285,8 +301,9 @@ static int v2_scratch(cs_graph* g, const CsV2Smem& M, int D, uint32_t grid, size
 }
 
 // Decide whether the shared-memory kernel serves this call and with which capacities: probe a strided sample of the
-// staged sources at the largest layout, then size pages / reached-node capacity with headroom.  Cached per
-// (max_seconds, speed, D).
+// staged sources at the largest layout (one CTA per SM), then size pages / reached-node capacity with a little headroom
+// so that two or more CTAs share an SM when the reach allows.  Sources that overflow the primary layout are re-run at
+// the largest layout, and only what overflows that goes to the global-arena kernel.  Cached per (max_seconds, speed, D).
 static int v2_plan(cs_graph* g, CsShortest2Params base, uint64_t m, uint32_t* launches) {
     auto& P = g->plan;
     if (P.valid && P.max_seconds == base.max_seconds && P.speed == base.speed && P.D == base.D && P.pb == g->opt_pb &&
@@ -302,13 +319,14 @@ static int v2_plan(cs_graph* g, CsShortest2Params base, uint64_t m, uint32_t* la
     if (!g->v2_ok || base.D > 8 || m == 0) return 0;
     CsV2Smem M;
     // largest layout that fits one CTA per SM
-    uint32_t rcap = 12288, pages = (uint32_t)(18432u >> g->opt_pb);
-    while (!(v2_layout(M, rcap, pages, g->opt_pb, base.D) && M.total <= CS2_SMEM_MAX)) {
-        rcap -= 1024;
-        pages = pages * 15 / 16;
+    uint32_t rcap = 16384, pages = (uint32_t)(24576u >> g->opt_pb);
+    while (!(v2_layout(M, rcap, pages, g->opt_pb, base.D, 256) && M.total <= CS2_SMEM_MAX)) {
+        rcap -= 512;
+        pages = pages * 31 / 32;
         if (rcap < 1024) return 0;
     }
-    const uint32_t count = (uint32_t)std::min<uint64_t>(m, 296);
+    P.sm_big = M;
+    const uint32_t count = (uint32_t)std::min<uint64_t>(m, 444);
     uint32_t* d_s = g->d_fb_sources;  // scratch for the sample
     float* d_w = g->d_fb_wt;
     cs_k_stride_sample<<<(count + 255) / 256, 256, 0, g->stream>>>(g->d_sources2, g->d_src_wt2, m, count, d_s, d_w);
@@ -321,12 +339,13 @@ static int v2_plan(cs_graph* g, CsShortest2Params base, uint64_t m, uint32_t* la
     p.src_wt = d_w;
     p.n_sources = count;
     p.probe_max = g->d_probe;
+    p.bin_scale = (float)M.NB / ((base.max_seconds + 1.0f) * (base.max_seconds + 1.0f));
     const uint32_t grid = std::min<uint32_t>(count, (uint32_t)g->sm_count);
     size_t stride = 0;
     if (v2_scratch(g, M, base.D, grid, &stride)) return 1;
     p.scratch = g->d_scratch2;
     p.scratch_stride = stride;
-    CS_CUDA(v2_launch(p, grid, g->stream, nullptr));
+    CS_CUDA(v2_launch(p, 256, grid, g->stream, nullptr));
     *launches += 2;
     uint32_t h[2] = {0, 0};
     CS_CUDA(cudaMemcpyAsync(h, g->d_probe, sizeof(h), cudaMemcpyDeviceToHost, g->stream));
@@ -334,25 +353,52 @@ static int v2_plan(cs_graph* g, CsShortest2Params base, uint64_t m, uint32_t* la
     CS_CUDA(cudaMemsetAsync(g->d_counters, 0, CS_NCOUNTERS * sizeof(unsigned long long), g->stream));
     P.probe_R = h[0];
     P.probe_pages = h[1];
-    if (h[0] == 0xffffffffu || h[1] == 0xffffffffu) {
-        // some sampled source does not fit even the largest layout: keep that layout; sources that overflow fall back
-        P.sm = M;
+    P.sm = M;
+    P.T = 512;
+    if (h[0] != 0xffffffffu && h[1] != 0xffffffffu) {
+        // (a sample that overflows even the largest layout keeps that layout; its sources fall back individually)
+        // Preference: several CTAs per SM (small reach: 128 threads; else 256 threads, shaving the capacity headroom
+        // if that is what it takes to fit two CTAs), otherwise one 512-thread CTA per SM.
+        const float heads[3] = {g->opt_headroom, 1.0f + (g->opt_headroom - 1.0f) * 0.6f, 1.0f + (g->opt_headroom - 1.0f) * 0.3f};
+        bool done = false;
+        for (int hi = 0; hi < 3 && !done; ++hi) {
+            const uint32_t want_r = std::min<uint32_t>(M.rcap, (uint32_t)(h[0] * heads[hi]) + 32);
+            const uint32_t want_p = (uint32_t)(h[1] * heads[hi]) + 4;
+            const int T = g->opt_threads ? g->opt_threads : (h[0] <= 1536 ? 128 : 256);
+            CsV2Smem M2;
+            if (!(v2_layout(M2, want_r, want_p, g->opt_pb, base.D, T) && M2.total <= M.total)) continue;
+            CsShortest2Params pt = base;
+            pt.sm = M2;
+            int occ2 = 0;
+            CS_CUDA(v2_launch(pt, T, 0, g->stream, &occ2));
+            if (occ2 >= 2 || g->opt_threads) {
+                P.sm = M2;
+                P.T = T;
+                done = true;
+            }
+        }
+        if (!done) {
+            const uint32_t want_r = std::min<uint32_t>(M.rcap, (uint32_t)(h[0] * g->opt_headroom) + 32);
+            const uint32_t want_p = (uint32_t)(h[1] * g->opt_headroom) + 4;
+            CsV2Smem M2;
+            if (v2_layout(M2, want_r, want_p, g->opt_pb, base.D, 512) && M2.total <= CS2_SMEM_MAX) P.sm = M2;
+            else v2_layout(P.sm, M.rcap, M.TB * 85 / 100, g->opt_pb, base.D, 512);
+        }
     } else {
-        const uint32_t want_r = std::min<uint32_t>(M.rcap, (uint32_t)(h[0] * 1.2) + 128);
-        const uint32_t want_p = (uint32_t)(h[1] * 1.2) + 16;
-        CsV2Smem M2;
-        if (v2_layout(M2, want_r, want_p, g->opt_pb, base.D) && M2.total <= M.total)
-            P.sm = M2;
-        else
-            P.sm = M;
+        v2_layout(P.sm, M.rcap, M.TB * 85 / 100, g->opt_pb, base.D, 512);
     }
     if (g->opt_reach_limit) {
         CsV2Smem M3;
-        if (v2_layout(M3, std::min(P.sm.rcap, g->opt_reach_limit), P.sm.TB, g->opt_pb, base.D) && M3.total <= CS2_SMEM_MAX) P.sm = M3;
+        if (v2_layout(M3, std::min(P.sm.rcap, g->opt_reach_limit), P.sm.TB, g->opt_pb, base.D, P.T) && M3.total <= CS2_SMEM_MAX) P.sm = M3;
+    }
+    if (g->opt_reach_limit2) {
+        CsV2Smem M4;
+        if (v2_layout(M4, std::min(P.sm_big.rcap, g->opt_reach_limit2), P.sm_big.TB, g->opt_pb, base.D, 256) && M4.total <= CS2_SMEM_MAX)
+            P.sm_big = M4;
     }
     p.sm = P.sm;
     int occ = 0;
-    CS_CUDA(v2_launch(p, 0, g->stream, &occ));
+    CS_CUDA(v2_launch(p, P.T, 0, g->stream, &occ));
     if (occ < 1) return 0;
     P.ctas_per_sm = occ;
     P.use = true;

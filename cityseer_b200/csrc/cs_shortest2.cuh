@@ -16,10 +16,13 @@
 #pragma once
 #include "cs_shortest.cuh"
 
-#define CS2_T 512             // threads per CTA (one source per CTA at a time)
-#define CS2_WARPS (CS2_T / 32)
+#define CS2_T_MAX 256         // threads per CTA (one source per CTA at a time): 128 or 256, template parameter T
 #define CS2_EMPTY 0xffffffffu
 #define CS2_MAX_DEG 8         // in/out degree bound of this kernel (4-bit fields, 8-bit predecessor masks)
+#ifndef CS2_POLL_NS
+#define CS2_POLL_NS 40        // back-off of a warp that found its in-chunk dependencies still pending
+#endif
+#define CS2_CHAIN_HOPS 12     // degree-2 nodes a search lane walks through before handing back to the queue
 
 struct CsV2Graph {
     uint32_t n;
@@ -113,14 +116,16 @@ __device__ __forceinline__ uint32_t cs2_bin(uint32_t ab, float bin_scale, uint32
     return min(NB - 1u, (uint32_t)(__fmul_rn(__fmul_rn(a, a), bin_scale)));
 }
 
-template <int DT>
-__global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Params p) {
+template <int DT, int T>
+__global__ void __launch_bounds__(T, T >= 512 ? 1 : 512 / T) cs_k_shortest2(const CsShortest2Params p) {
+    constexpr uint32_t CS2_T = T;
+    constexpr uint32_t CS2_WARPS = T / 32;
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_cnt[3];       // rotating near-queue counters
     __shared__ uint32_t s_npages, s_min, s_R, s_maxgap;
     __shared__ int s_fail;
     __shared__ unsigned long long s_si;
-    __shared__ uint32_t s_histN[CS_MAX_THRESHOLDS + 1], s_histE[CS_MAX_THRESHOLDS + 1];
+    __shared__ uint32_t s_histE[CS_MAX_THRESHOLDS + 1];
     __shared__ float s_rankf[CS_MAX_THRESHOLDS];
     __shared__ uint32_t s_scan[CS2_WARPS];
 
@@ -133,8 +138,8 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
     uint32_t* s_defer = reinterpret_cast<uint32_t*>(smem + M.off_defer);
     uint16_t* s_rank = reinterpret_cast<uint16_t*>(smem + M.off_rank);
     uint16_t* s_perm = reinterpret_cast<uint16_t*>(smem + M.off_perm);
-    uint8_t* s_pmask = smem + M.off_pmask;
     uint8_t* s_u = smem + M.off_u;
+    uint8_t* s_pmask = smem + M.off_pmask;  // inside the union region, behind the sigma ring (written from P3 on)
     // P1 view of the union region: two queues of three words per item
     uint32_t* qbase = reinterpret_cast<uint32_t*>(s_u);
     // P2 view: bins[NB + 1], tmp u16[rcap]
@@ -145,7 +150,6 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
     // P5 view: ring of {sigma, dep[2D]} entries + done flags
     const int D = p.D, D2 = 2 * D, ES = D2 + 1;
     volatile double* s_dep = reinterpret_cast<volatile double*>(smem + M.off_dep);
-    volatile uint32_t* s_done = reinterpret_cast<volatile uint32_t*>(smem + M.off_dep + (size_t)WD * ES * 8);
 
     uint8_t* scr = p.scratch + (size_t)blockIdx.x * p.scratch_stride;
     uint32_t* g_agg = reinterpret_cast<uint32_t*>(scr);
@@ -172,7 +176,6 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
         for (uint32_t i = tid; i < TB; i += CS2_T) s_keys[i] = CS2_EMPTY;
         for (uint32_t i = tid; i < S / 32; i += CS2_T) s_defer[i] = 0;
         if (tid <= CS_MAX_THRESHOLDS) {
-            s_histN[tid] = 0;
             s_histE[tid] = 0;
         }
         if (tid == 0) {
@@ -201,6 +204,9 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
         {
             float thr = p.delta;
             uint32_t it = 0;  // iteration counter selects the rotating queue / counter
+            uint32_t n_split = 0;
+            const long long t_p1 = clock64();
+            long long t_split = 0, t_s0 = 0;
             for (;;) {
                 for (;;) {
                     const uint32_t cur = it % 3u, nxt = (it + 1u) % 3u;
@@ -250,26 +256,36 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
                             bool pn = false;
                             uint32_t i0 = 0, i1 = 0, i2 = 0, dslot = 0;
                             if (j < deg && j + 1u != skip) {
-                                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&p.g.in2[eb + j]));
-                                const float cand = __fadd_rn(a, __uint_as_float(raw.y));
-                                if (!(raw.w & 0x200u) && !(cand > p.max_seconds)) {
+                                uint4 raw = __ldg(reinterpret_cast<const uint4*>(&p.g.in2[eb + j]));
+                                float from = a;
+                                for (int hop = 0;; ++hop) {
+                                    const float cand = __fadd_rn(from, __uint_as_float(raw.y));
+                                    if ((raw.w & 0x200u) || cand > p.max_seconds) break;
                                     const uint32_t cbits = __float_as_uint(cand);
                                     const uint32_t nb = raw.x;
                                     const uint32_t page = cs2_map_insert(s_keys, TB, nb >> pb, M.max_pages, &s_npages, &s_fail);
                                     const uint32_t nslot = (page << pb) | (nb & pm);
                                     const uint32_t old = atomicMin(&s_dist[nslot], cbits);
-                                    if (cbits < old) {
-                                        ++relax;
-                                        if (cand < thr) {
-                                            pn = true;
-                                            i0 = nslot | (((raw.w >> 24) & 0xfu) << 16) | (((raw.w >> 16) & 0xfu) << 20);
-                                            i1 = cbits;
-                                            i2 = raw.z;
-                                        } else {
-                                            atomicOr(&s_defer[nslot >> 5], 1u << (nslot & 31u));
-                                        }
-                                        dslot = nslot;
+                                    if (!(cbits < old)) break;
+                                    ++relax;
+                                    if (!(cand < thr)) {
+                                        atomicOr(&s_defer[nslot >> 5], 1u << (nslot & 31u));
+                                        break;
                                     }
+                                    const uint32_t ndeg = (raw.w >> 24) & 0xfu, back = (raw.w >> 16) & 0xfu;
+                                    if (ndeg == 2u && back != 0u && hop < CS2_CHAIN_HOPS) {
+                                        // degree-2 node: its only other incoming edge continues the chain; relax it here
+                                        // instead of paying a queue round trip per 20 m segment of a decomposed street
+                                        raw = __ldg(reinterpret_cast<const uint4*>(&p.g.in2[raw.z + ((back - 1u) ^ 1u)]));
+                                        from = cand;
+                                        continue;
+                                    }
+                                    pn = true;
+                                    i0 = nslot | (ndeg << 16) | (back << 20);
+                                    i1 = cbits;
+                                    i2 = raw.z;
+                                    dslot = nslot;
+                                    break;
                                 }
                             }
                             const uint32_t m = __ballot_sync(CS_FULL, pn);
@@ -296,6 +312,7 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
                 }
                 // near bucket exhausted (all threads saw nc == 0 after the same barrier)
                 if (s_fail) break;
+                t_s0 = clock64();
                 // pass 1: smallest deferred distance
                 __syncthreads();
                 if (tid == 0) s_min = CS_INF_BITS;
@@ -313,6 +330,7 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
                 const uint32_t mnb = s_min;
                 if (mnb == CS_INF_BITS) break;
                 thr = __uint_as_float(mnb) + p.delta;
+                ++n_split;
                 // pass 2: move the deferred slots below the new threshold into the current queue
                 {
                     const uint32_t cur = it % 3u;
@@ -345,6 +363,13 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
                     }
                 }
                 __syncthreads();
+                t_split += clock64() - t_s0;
+            }
+            if (tid == 0) {
+                atomicAdd(&p.counters[CS_C_PHASE0 + 6], (unsigned long long)it);
+                atomicAdd(&p.counters[CS_C_PHASE0 + 7], (unsigned long long)n_split);
+                atomicAdd(&p.counters[CS_C_PHASE0 + 5], (unsigned long long)t_split);      // debug: split cycles
+                atomicAdd(&p.counters[CS_C_REACH0 + 15], (unsigned long long)(t_p1 - tc[0]));  // debug: init cycles
             }
         }
         __syncthreads();
@@ -460,15 +485,15 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
             uint32_t cu[CS2_MAX_DEG], crk[CS2_MAX_DEG], cj[CS2_MAX_DEG];
             int ncand = 0;
             uint32_t pmask_c = 0;
-            int tiN = -1;
-            uint32_t eh[CS2_MAX_DEG];  // circuit-rank histogram targets of this node's canonical edges
-            int neh = 0;
+            constexpr int NEW = (DT + 1 + 3) / 4;
+            unsigned long long ep[NEW];  // circuit-rank edge histogram of this node, 16 bits per threshold bin
+#pragma unroll
+            for (int k = 0; k < NEW; ++k) ep[k] = 0ull;
             if (valid) {
                 const uint32_t slot = s_perm[r];
                 v = (s_keys[slot >> pb] << pb) | (slot & pm);
                 const float av = __uint_as_float(s_dist[slot]);
                 const float cost_v = __fmul_rn(av, p.speed);
-                if (p.closeness) tiN = cs2_first_threshold<DT>(p, cost_v);
                 const uint4 nd = __ldg(&p.g.node2[v]);
                 const uint32_t eb = nd.y, deg = (nd.z >> 8) & 0xffu;
                 edge_iters += nd.z & 0xffu;
@@ -484,7 +509,10 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
                     const float au = __uint_as_float(ub);
                     if (p.closeness && (raw.w & 0x100u)) {
                         const float ec = fmaxf(cost_v, __fmul_rn(au, p.speed));
-                        eh[neh++] = (uint32_t)cs2_first_threshold<DT>(p, ec);
+                        const int t = cs2_first_threshold<DT>(p, ec);
+#pragma unroll
+                        for (int k = 0; k < NEW; ++k)
+                            if ((t >> 2) == k) ep[k] += 1ull << ((t & 3) * 16);
                     }
                     const uint32_t urank = s_rank[uslot];
                     if (urank >= r || v == src) continue;  // u must be settled before v; the source has no predecessors
@@ -542,29 +570,56 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
                 if (gap > s_maxgap) atomicMax(&s_maxgap, gap);
                 if (p.dump_npred) p.dump_npred[__ldg(&p.g.orig_of_new[v])] = __popc(pmask_c);
             }
-            // circuit-rank histograms, aggregated per warp (one shared-memory atomic per warp and bin)
+            // circuit-rank edge histogram, aggregated per warp (one shared-memory atomic per warp and non-empty bin)
             if (p.closeness) {
-                for (int t = 0; t <= D; ++t) {
-                    const uint32_t mN = __ballot_sync(CS_FULL, tiN == t);
-                    uint32_t ce = 0;
-                    for (int k = 0; k < neh; ++k) ce += eh[k] == (uint32_t)t ? 1u : 0u;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) ce += __shfl_xor_sync(CS_FULL, ce, o);
-                    if (lane == 0) {
-                        if (mN) atomicAdd(&s_histN[t], (uint32_t)__popc(mN));
-                        if (ce) atomicAdd(&s_histE[t], ce);
+                for (int k = 0; k < NEW; ++k) {
+                    unsigned long long e = ep[k];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(CS_FULL, e, o);
+                    if (lane == 0 && e) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const uint32_t c = (uint32_t)(e >> (16 * b)) & 0xffffu;
+                            if (c && 4 * k + b <= D) atomicAdd(&s_histE[4 * k + b], c);
+                        }
                     }
                 }
             }
             // sigma = sum over predecessors in settle order; predecessors of this chunk may still be pending (ring == 0)
             bool pending = valid;
             const uint32_t ring_lo = b0 + 2u * CS2_T >= WS ? b0 + 2u * CS2_T - WS : 0u;  // older ranks: read global
+            // predecessor ranks in registers (two cover almost every node; more take the generic path)
+            uint32_t pr0 = CS2_EMPTY, pr1 = CS2_EMPTY;
+            const bool pmany = __popc(pmask_c) > 2;
+            if (pmask_c) {
+                pr0 = crk[__ffs(pmask_c) - 1];
+                const uint32_t rest = pmask_c & (pmask_c - 1);
+                if (rest) pr1 = crk[__ffs(rest) - 1];
+            }
+            double sfar = 0.0;  // predecessors older than the ring: final, read once from global
+            if (pr0 != CS2_EMPTY && pr0 < ring_lo) {
+                sfar += __ldcg(&g_sigma[pr0]);
+                pr0 = CS2_EMPTY;
+            }
+            if (pr1 != CS2_EMPTY && pr1 < ring_lo) {
+                sfar += __ldcg(&g_sigma[pr1]);
+                pr1 = CS2_EMPTY;
+            }
             for (;;) {
                 if (pending) {
                     double s = 0.0;
                     bool ok = true;
                     if (v == src) {
                         s = 1.0;
+                    } else if (!pmany) {
+                        // summation order = settle order of the predecessors (pr0 before pr1), far ones first
+                        const double s0 = pr0 != CS2_EMPTY ? s_sig[pr0 % WS] : 1.0;
+                        const double s1 = pr1 != CS2_EMPTY ? s_sig[pr1 % WS] : 1.0;
+                        ok = s0 != 0.0 && s1 != 0.0;
+                        s = sfar;
+                        if (pr0 != CS2_EMPTY) s += s0;
+                        if (pr1 != CS2_EMPTY) s += s1;
                     } else {
                         for (uint32_t mm = pmask_c; mm; mm &= mm - 1) {
                             const uint32_t ur = crk[__ffs(mm) - 1];
@@ -590,6 +645,7 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
                 }
                 __syncwarp();
                 if (!__any_sync(CS_FULL, pending)) break;
+                __nanosleep(CS2_POLL_NS);
             }
         }
         __syncthreads();
@@ -607,12 +663,17 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
         unsigned long long n_ri = 0, n_ci = 0;
         if (p.closeness) {
             if (tid < (uint32_t)D) {
-                // circuit rank per threshold = max(0, E_i - N_i + 1) over the reached subgraph (centrality.rs:517-525)
-                long long ncount = 0, ecount = 0;
-                for (int t = 0; t <= (int)tid; ++t) {
-                    ncount += s_histN[t];
-                    ecount += s_histE[t];
+                // circuit rank per threshold = max(0, E_i - N_i + 1) over the reached subgraph (centrality.rs:517-525);
+                // N_i = reached nodes with cost <= d_i = an upper bound in the settle order (cost is monotone in rank)
+                uint32_t lo = 0, hi = R;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    const float c = __fmul_rn(__uint_as_float(s_dist[s_perm[mid]]), p.speed);
+                    if (c <= p.dist_f[tid]) lo = mid + 1; else hi = mid;
                 }
+                const long long ncount = lo;
+                long long ecount = 0;
+                for (int t = 0; t <= (int)tid; ++t) ecount += s_histE[t];
                 s_rankf[tid] = ncount == 0 ? 0.0f : (float)max(ecount - ncount + 1ll, 0ll);
                 atomicAdd(&p.counters[CS_C_REACH0 + tid], (unsigned long long)(ncount > 0 ? ncount - 1 : 0));
             }
@@ -679,109 +740,186 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
         if (p.betweenness) {
             const double wt_d = (double)wt;
             const bool far_deps = s_maxgap + CS2_T >= WD;  // some successor may lie beyond the ring: write dependencies through
-            for (int b0 = (int)((R - 1) / CS2_T * CS2_T); b0 >= 0; b0 -= CS2_T) {
+            for (int b0 = (int)((R - 1) / CS2_T * CS2_T); b0 >= 0; b0 -= (int)CS2_T) {
                 const uint32_t r = (uint32_t)b0 + tid;
                 const bool valid = r < R;
                 __syncthreads();  // every reader of the previous chunk is done with the entries recycled below
+#ifdef CS2_DEBUG_CLOCKS
+                long long tq[6];
+                tq[0] = clock64();
+#endif
                 double sigma_w = 1.0;
                 float cost_w = 0.f;
+                const long long SENT = -1ll;  // "not yet written" pattern of a ring word (a NaN no dependency can equal)
                 if (valid) {
                     sigma_w = __ldcg(&g_sigma[r]);
                     cost_w = __fmul_rn(__uint_as_float(__ldcg(&g_agg[r])), p.speed);
-                    s_dep[(size_t)(r % WD) * ES] = sigma_w;
-                    s_done[r % WD] = 0u;
+                    volatile double* er0 = s_dep + (size_t)(r % WD) * ES;
+                    er0[0] = sigma_w;
+                    for (int i = 1; i <= D2; ++i) er0[i] = __longlong_as_double(SENT);
                 }
                 __syncthreads();
+#ifdef CS2_DEBUG_CLOCKS
+                tq[1] = clock64();
+#endif
                 uint32_t w = 0;
-                uint32_t srk[CS2_MAX_DEG];
-                int nsucc = 0;
-                uint32_t same_chunk = 0;  // successors inside this chunk (the only ones that can still be pending)
+                // successors by in-list position (static indexing keeps them in registers); CS2_EMPTY = none
+                uint32_t sr[CS2_MAX_DEG];
+                double fr[CS2_MAX_DEG];
+#pragma unroll
+                for (int j = 0; j < CS2_MAX_DEG; ++j) sr[j] = CS2_EMPTY;
+                double accf[DT], accbf[DT];  // contributions of successors beyond the ring (read from global once)
+#pragma unroll
+                for (int i = 0; i < DT; ++i) accf[i] = accbf[i] = 0.0;
                 if (valid) {
                     const uint32_t slot = s_perm[r];
                     w = (s_keys[slot >> pb] << pb) | (slot & pm);
                     const uint4 nd = __ldg(&p.g.node2[w]);
                     const uint32_t eb = nd.x, deg = nd.z & 0xffu;
-                    for (uint32_t j = 0; j < deg; ++j) {
-                        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&p.g.in2[eb + j]));
-                        const uint32_t x = raw.x;
-                        if (x == w) continue;
-                        const uint32_t xpage = cs2_map_find(s_keys, TB, x >> pb);
-                        if (xpage == CS2_EMPTY) continue;
-                        const uint32_t xslot = (xpage << pb) | (x & pm);
-                        const uint32_t xr = s_rank[xslot];
-                        // s_dist may be recycled: "reached" is decided by the permutation (rank valid and maps back)
-                        if (xr >= R || s_perm[xr] != xslot || xr <= r) continue;
-                        if ((s_pmask[xr] >> (raw.w & 0xffu)) & 1u) {
-                            if (xr < (uint32_t)b0 + CS2_T) same_chunk |= 1u << nsucc;
-                            srk[nsucc++] = xr;
-                        }
-                    }
-                }
-                bool pending = valid;
-                double cr[2 * DT];  // positive credits of this thread's node, slot 2 * i (plain) / 2 * i + 1 (beta-weighted)
 #pragma unroll
-                for (int q = 0; q < 2 * DT; ++q) cr[q] = 0.0;
-                for (;;) {
-                    if (pending) {
-                        bool ok = true;
-                        for (uint32_t mm = same_chunk; mm; mm &= mm - 1) ok = ok && (s_done[srk[__ffs(mm) - 1] % WD] != 0u);
-                        if (ok) {
-                            __threadfence_block();
-                            double acc[DT], accb[DT];
+                    for (int j = 0; j < CS2_MAX_DEG; ++j) {
+                        if ((uint32_t)j < deg) {
+                            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&p.g.in2[eb + j]));
+                            const uint32_t x = raw.x;
+                            const uint32_t xpage = x == w ? CS2_EMPTY : cs2_map_find(s_keys, TB, x >> pb);
+                            if (xpage != CS2_EMPTY) {
+                                const uint32_t xslot = (xpage << pb) | (x & pm);
+                                const uint32_t xr = s_rank[xslot];
+                                // s_dist may be recycled: "reached" is decided by the permutation (rank valid and maps back)
+                                if (xr < R && xr > r && s_perm[xr] == xslot && ((s_pmask[xr] >> (raw.w & 0xffu)) & 1u)) {
+                                    const bool in_ring = xr < (uint32_t)b0 + WD;
+                                    const double sx = in_ring ? s_dep[(size_t)(xr % WD) * ES] : __ldcg(&g_sigma[xr]);
+                                    const double f = (sx == sigma_w) ? 1.0 : sigma_w / sx;  // centrality.rs:861-866
+                                    if (in_ring) {
+                                        sr[j] = xr;
+                                        fr[j] = f;
+                                    } else {
+                                        const double* gx = g_dep + (size_t)xr * D2;
 #pragma unroll
-                            for (int i = 0; i < DT; ++i) acc[i] = accb[i] = 0.0;
-                            for (int k = 0; k < nsucc; ++k) {
-                                const uint32_t xr = srk[k];
-                                const bool in_ring = xr < (uint32_t)b0 + WD;
-                                const volatile double* e = s_dep + (size_t)(xr % WD) * ES;
-                                const double sx = in_ring ? e[0] : __ldcg(&g_sigma[xr]);
-                                const double f = (sx == sigma_w) ? 1.0 : sigma_w / sx;
-                                const double* gx = g_dep + (size_t)xr * D2;
-#pragma unroll
-                                for (int i = 0; i < DT; ++i) {
-                                    if (i < D) {
-                                        acc[i] += f * (in_ring ? e[1 + i] : __ldcg(&gx[i]));
-                                        accb[i] += f * (in_ring ? e[1 + D + i] : __ldcg(&gx[D + i]));
-                                    }
-                                }
-                            }
-                            const bool is_src = (w == src);
-                            const double pc = is_src ? 0.0 : (__ldg(&p.eligible[w]) ? 0.5 : 1.0);
-                            volatile double* er = s_dep + (size_t)(r % WD) * ES;
-                            double* gr = g_dep + (size_t)r * D2;
-#pragma unroll
-                            for (int i = 0; i < DT; ++i) {
-                                if (i < D) {
-                                    double seed = 0.0, seedb = 0.0;
-                                    if (!is_src && cost_w <= p.dist_f[i]) {
-                                        seed = pc;
-                                        seedb = pc * exp(-p.beta_d[i] * (double)cost_w);
-                                    }
-                                    const double dpn = seed + acc[i], dpb = seedb + accb[i];
-                                    er[1 + i] = dpn;
-                                    er[1 + D + i] = dpb;
-                                    if (far_deps) {
-                                        __stcg(&gr[i], dpn);
-                                        __stcg(&gr[D + i], dpb);
-                                    }
-                                    if (!is_src) {
-                                        const double credit = dpn - seed, creditb = dpb - seedb;
-                                        if (credit > 0.0 || creditb > 0.0) {
-                                            ++n_ci;
-                                            if (credit > 0.0) cr[2 * i] = credit * wt_d;
-                                            if (creditb > 0.0) cr[2 * i + 1] = creditb * wt_d;
+                                        for (int i = 0; i < DT; ++i) {
+                                            if (i < D) {
+                                                accf[i] += f * __ldcg(&gx[i]);
+                                                accbf[i] += f * __ldcg(&gx[D + i]);
+                                            }
                                         }
                                     }
                                 }
                             }
-                            __threadfence_block();
-                            s_done[r % WD] = 1u;
-                            pending = false;
+                        }
+                    }
+                }
+#ifdef CS2_DEBUG_CLOCKS
+                tq[2] = clock64();
+#endif
+                bool pending = valid;
+                double cr[2 * DT];  // positive credits of this thread's node, slot 2 * i (plain) / 2 * i + 1 (beta-weighted)
+#pragma unroll
+                for (int q = 0; q < 2 * DT; ++q) cr[q] = 0.0;
+                // seeds do not depend on the successors either (centrality.rs:1802-1806, f64 exp)
+                const bool is_src = (w == src);
+                double seed[DT], seedb[DT];
+#pragma unroll
+                for (int i = 0; i < DT; ++i) seed[i] = seedb[i] = 0.0;
+                if (valid && !is_src) {
+                    const double pc = __ldg(&p.eligible[w]) ? 0.5 : 1.0;
+#pragma unroll
+                    for (int i = 0; i < DT; ++i) {
+                        if (i < D && cost_w <= p.dist_f[i]) {
+                            seed[i] = pc;
+                            seedb[i] = pc * exp(-p.beta_d[i] * (double)cost_w);
+                        }
+                    }
+                }
+                // Wait for the successors of this chunk.  A ring word is either the sentinel or final (8-byte stores are
+                // single transactions), so readiness is read off the values themselves: no flags, no fences.
+#ifdef CS2_DEBUG_CLOCKS
+                tq[3] = clock64();
+#endif
+                // probe words (ring word 1) of the successors that sit in this chunk: the only ones that can be pending
+                uint32_t pa0 = CS2_EMPTY, pa1 = CS2_EMPTY;
+                bool pmany = false;
+#pragma unroll
+                for (int j = 0; j < CS2_MAX_DEG; ++j) {
+                    if (sr[j] != CS2_EMPTY && sr[j] < (uint32_t)b0 + CS2_T) {
+                        const uint32_t ix = (sr[j] % WD) * ES + 1u;
+                        if (pa0 == CS2_EMPTY) pa0 = ix;
+                        else if (pa1 == CS2_EMPTY) pa1 = ix;
+                        else pmany = true;
+                    }
+                }
+                for (;;) {
+                    if (pending) {
+                        bool ok = (pa0 == CS2_EMPTY || __double_as_longlong(s_dep[pa0]) != SENT) &&
+                                  (pa1 == CS2_EMPTY || __double_as_longlong(s_dep[pa1]) != SENT);
+                        if (ok && pmany) {
+#pragma unroll
+                            for (int j = 0; j < CS2_MAX_DEG; ++j) {
+                                if (sr[j] != CS2_EMPTY && sr[j] < (uint32_t)b0 + CS2_T)
+                                    ok = ok && (__double_as_longlong(s_dep[(size_t)(sr[j] % WD) * ES + 1]) != SENT);
+                            }
+                        }
+                        if (ok) {
+                            double acc[DT], accb[DT];
+#pragma unroll
+                            for (int i = 0; i < DT; ++i) {
+                                acc[i] = accf[i];
+                                accb[i] = accbf[i];
+                            }
+#pragma unroll
+                            for (int j = 0; j < CS2_MAX_DEG; ++j) {
+                                if (sr[j] != CS2_EMPTY) {
+                                    const volatile double* e = s_dep + (size_t)(sr[j] % WD) * ES;
+#pragma unroll
+                                    for (int i = 0; i < DT; ++i) {
+                                        if (i < D) {
+                                            const double a0 = e[1 + i], a1 = e[1 + D + i];
+                                            ok = ok && (__double_as_longlong(a0) != SENT) && (__double_as_longlong(a1) != SENT);
+                                            acc[i] += fr[j] * a0;
+                                            accb[i] += fr[j] * a1;
+                                        }
+                                    }
+                                }
+                            }
+                            if (ok) {
+                                volatile double* er = s_dep + (size_t)(r % WD) * ES;
+#pragma unroll
+                                for (int i = DT - 1; i >= 0; --i) {
+                                    if (i < D) {
+                                        er[1 + D + i] = seedb[i] + accb[i];
+                                        er[1 + i] = seed[i] + acc[i];  // word 1 is written last: the cheap readiness probe
+                                    }
+                                }
+                                pending = false;
+                                // off the critical path: write-through for far readers and the credits
+                                double* gr = g_dep + (size_t)r * D2;
+#pragma unroll
+                                for (int i = 0; i < DT; ++i) {
+                                    if (i < D) {
+                                        const double dpn = seed[i] + acc[i], dpb = seedb[i] + accb[i];
+                                        if (far_deps) {
+                                            __stcg(&gr[i], dpn);
+                                            __stcg(&gr[D + i], dpb);
+                                        }
+                                        if (!is_src) {
+                                            const double credit = dpn - seed[i], creditb = dpb - seedb[i];
+                                            if (credit > 0.0 || creditb > 0.0) {
+                                                ++n_ci;
+                                                if (credit > 0.0) cr[2 * i] = credit * wt_d;
+                                                if (creditb > 0.0) cr[2 * i + 1] = creditb * wt_d;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
                         }
                     }
                     __syncwarp();
                     if (!__any_sync(CS_FULL, pending)) break;
+                    __nanosleep(CS2_POLL_NS);  // waiting warps leave the issue slots to the warps that make progress
                 }
+#ifdef CS2_DEBUG_CLOCKS
+                tq[4] = clock64();
+#endif
                 // packed credit scatter: 32/LPB nodes per warp instruction, LPB consecutive doubles each
                 {
                     constexpr int NQB = 2 * DT;
@@ -802,6 +940,11 @@ __global__ void __launch_bounds__(CS2_T, 1) cs_k_shortest2(const CsShortest2Para
                         if (val > 0.0) cs_red_add(p.acc_b + (size_t)nd * p.bw + q, val);
                     }
                 }
+#ifdef CS2_DEBUG_CLOCKS
+                tq[5] = clock64();
+                if (tid == 0)
+                    for (int k = 0; k < 5; ++k) atomicAdd(&p.counters[CS_C_REACH0 + 10 + k], (unsigned long long)(tq[k + 1] - tq[k]));
+#endif
             }
         }
         tc[5] = clock64();

@@ -38,8 +38,12 @@ typedef struct cs_stats {
     uint32_t gpu_launches;    /* kernels launched by this call */
     uint32_t workers;         /* resident workers (warps or CTAs, one source each at a time) */
     uint64_t phase_cycles[8]; /* SM clock cycles summed over workers per kernel phase (search, order, predecessors,
-                                 closeness, dependencies, reset, 2 spare): where the kernel's time goes */
+                                 closeness, dependencies, reset); [6], [7]: search iterations and bucket advances of the shared-memory kernel */
     uint64_t fallback_sources; /* sources the shared-memory kernel handed to the global-arena kernel (capacity overflow) */
+    uint32_t smem_bytes;      /* shared-memory kernel: dynamic shared memory per CTA (0 = global-arena kernel ran) */
+    uint32_t ctas_per_sm;     /* shared-memory kernel: resident CTAs per SM */
+    uint32_t reach_capacity;  /* shared-memory kernel: reached nodes per source it can hold */
+    uint32_t slot_capacity;   /* shared-memory kernel: distance-map slots (pages x page size) */
 } cs_stats;
 
 const char* cs_last_error(void);

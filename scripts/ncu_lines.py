@@ -34,7 +34,7 @@ for ln in dis:
     if m:
         cur = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
-    if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+    if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
         lines.append(cur)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kname}"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))

@@ -23,6 +23,7 @@ ap.add_argument("--closeness", type=int, default=1)
 ap.add_argument("--betweenness", type=int, default=1)
 ap.add_argument("--distances", default="500,1000,2000")
 ap.add_argument("--fn", default="shortest", choices=["shortest", "segment", "simplest"])
+ap.add_argument("--opt", action="append", default=[], help="name=value device option (cs_graph_set_option)")
 a = ap.parse_args()
 t = time.time()
 ns, info = synth.config(a.cfg, a.scale)
@@ -32,6 +33,9 @@ dev = ns.device_graph()
 print(f"upload {time.time() - t:.2f}s", flush=True)
 if a.delta or a.workers:
     dev.configure(0, a.delta, a.workers)
+for o in a.opt:
+    k, v = o.split("=")
+    dev.set_option(k, float(v))
 kw = {}
 if a.nsrc:
     rng = np.random.default_rng(7)
@@ -55,5 +59,9 @@ for rep in range(a.reps):
                       "gteps": s["edge_iters"] / (s["kernel_ms"] / 1e3) / 1e9, "R": s["settled"] / max(1, s["sources"]),
                       "relax_per_settled": s["relaxations"] / max(1, s["settled"]), "workers": s["workers"],
                       "fallback": s["fallback_sources"],
-                      "phase_pct": [round(100.0 * c / max(1, sum(s["phase_cycles"])), 1) for c in s["phase_cycles"]],
-                      "cycles_per_source": sum(s["phase_cycles"]) / max(1, s["sources"])}), flush=True)
+                      "phase_pct": [round(100.0 * c / max(1, sum(s["phase_cycles"][:6])), 1) for c in s["phase_cycles"][:6]],
+                      "cycles_per_source": sum(s["phase_cycles"][:5]) / max(1, s["sources"]),
+                      "init_kcyc": round(s["dbg15"] / max(1, s["sources"]) / 1e3, 1), "dbg_kcyc": [round(c / max(1, s["sources"]) / 1e3, 1) for c in s["dbg"]], "phase_kcyc": [round(c / max(1, s["sources"]) / 1e3, 1) for c in s["phase_cycles"][:6]],
+                      "p1_iters": s["phase_cycles"][6] / max(1, s["sources"]), "p1_splits": s["phase_cycles"][7] / max(1, s["sources"]),
+                      "smem": s["smem_bytes"], "ctas_per_sm": s["ctas_per_sm"], "rcap": s["reach_capacity"],
+                      "slots": s["slot_capacity"]}), flush=True)

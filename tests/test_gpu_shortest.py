@@ -214,14 +214,30 @@ def test_linearity_property_full_size_graph():
     np.testing.assert_allclose(a._out[1] + b._out[1], full._out[1], rtol=1e-9)
 
 
-def test_smem_kernel_overflow_falls_back_to_arena_kernel(oracle_mod, kernel_choice):
-    # sources whose reach exceeds the shared-memory capacity are re-run by the global-arena kernel and added on top
+@pytest.mark.parametrize("limit2", [0, 512], ids=["second-pass", "second-pass+arena"])
+def test_smem_kernel_overflow_paths(oracle_mod, kernel_choice, limit2):
+    # sources whose reach exceeds the primary shared-memory layout are re-run at the largest layout, and what overflows
+    # that is re-run by the global-arena kernel; every path adds into the same result
     if kernel_choice != 2:
         pytest.skip("shared-memory kernel only")
     ns, _ = synth.config("cfg2", 0.2)
     dev = ns.device_graph()
     dev.set_option("smem_reach_limit", 256)
+    if limit2:
+        dev.set_option("smem_reach_limit2", limit2)
     res, ref, cnt = run_both(oracle_mod, ns, [500, 1000, 2000])
     check(res._out, ref)
     assert 0 < res.stats["fallback_sources"] < res.stats["sources"]
+    assert res.stats["settled"] == cnt["settled"] and res.stats["sum_ci"] == cnt["sum_ci"]
+    assert res.stats["sum_ri"] == cnt["sum_ri"] and res.stats["edge_iters"] == cnt["edge_iters"]
+
+
+@pytest.mark.parametrize("threads", [128, 256])
+def test_smem_kernel_thread_counts(oracle_mod, kernel_choice, threads):
+    if kernel_choice != 2:
+        pytest.skip("shared-memory kernel only")
+    ns, _ = synth.config("cfg4", 0.06)
+    ns.device_graph().set_option("threads", threads)
+    res, ref, cnt = run_both(oracle_mod, ns, [500, 1000, 2000])
+    check(res._out, ref)
     assert res.stats["settled"] == cnt["settled"] and res.stats["sum_ci"] == cnt["sum_ci"]
