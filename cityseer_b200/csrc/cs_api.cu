@@ -107,7 +107,7 @@ struct cs_graph {
         uint64_t n_sources = 0;
         CsV2Smem sm{}, sm_big{};
     } plan;
-    int opt_kernel = 0;  // 0 auto, 1 global-arena kernel only, 2 shared-memory kernel required
+    int opt_kernel = 0;  // 0 auto (= global-arena kernel, the faster one as measured), 1 global-arena kernel, 2 shared-memory kernel
     uint32_t opt_pb = 3;
     float opt_delta_factor = 12.0f;
     float opt_headroom = 1.1f;  // capacity of the primary shared-memory layout relative to the probed maxima
@@ -768,7 +768,7 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
     // ---- shared-memory kernel (cs_shortest2.cuh) when the graph and the call fit it
     bool use_v2 = false;
     CsShortest2Params q{};
-    if (g->opt_kernel != 1 && g->v2_ok && D <= 8 && n_sources > 0) {
+    if (g->opt_kernel == 2 && g->v2_ok && D <= 8 && n_sources > 0) {  // auto = the arena kernel: measured faster (profiles/r01d)
         if (stage_sources_v2(g, n_sources, &launches)) return 1;
         if (g->cached_speed2 != speed && g->E) {
             const int blocks = (int)((g->E + 255) / 256);
