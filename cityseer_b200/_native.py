@@ -42,6 +42,8 @@ class CsStats(C.Structure):
         ("ctas_per_sm", C.c_uint32),
         ("reach_capacity", C.c_uint32),
         ("slot_capacity", C.c_uint32),
+        ("kernel_used", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 
@@ -234,6 +236,7 @@ class DeviceGraph:
             "ctas_per_sm": int(st.ctas_per_sm),
             "reach_capacity": int(st.reach_capacity),
             "slot_capacity": int(st.slot_capacity),
+            "kernel_used": int(st.kernel_used),
         }
 
     def _thresholds(self, d, b, s):

@@ -14,6 +14,7 @@
 
 #include "cs_shortest.cuh"
 #include "cs_shortest2.cuh"
+#include "cs_shortest3.cuh"
 #include "cs_segment.cuh"
 #include "cs_simplest.cuh"
 
@@ -107,7 +108,19 @@ struct cs_graph {
         uint64_t n_sources = 0;
         CsV2Smem sm{}, sm_big{};
     } plan;
-    int opt_kernel = 0;  // 0 auto (= global-arena kernel, the faster one as measured), 1 global-arena kernel, 2 shared-memory kernel
+    // chain-contracted kernel (cs_shortest3.cuh)
+    bool v3_ok = false;
+    uint32_t v3_J = 0, v3_I = 0;
+    size_t v3_ncsec = 0;
+    uint2* d3_jinfo = nullptr;
+    uint4 *d3_links = nullptr, *d3_ctab = nullptr;
+    float *d3_cnum = nullptr, *d3_csec = nullptr, *d3_weight = nullptr;
+    uint32_t *d3_int_chain = nullptr, *d3_orig_of_new = nullptr, *d3_new_of_orig = nullptr;
+    uint8_t* d3_eligible = nullptr;
+    float cached_speed3 = -1.f;
+    int last_kernel = 1;
+    int opt_kernel = 0;  // 0 auto (chain-contracted kernel when the graph qualifies, else the global-arena kernel),
+                         // 1 global-arena kernel, 2 shared-memory kernel, 3 chain-contracted kernel (required)
     uint32_t opt_pb = 3;
     float opt_delta_factor = 12.0f;
     float opt_headroom = 1.1f;  // capacity of the primary shared-memory layout relative to the probed maxima
@@ -156,6 +169,11 @@ static int build_v2_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, c
                           const std::vector<CsEdge>& in_rec, const std::vector<CsEdge>& out_rec,
                           const std::vector<float>& in_num, const std::vector<float>& out_num,
                           const std::vector<float>& weight, const std::vector<uint8_t>& live, uint32_t max_deg);
+static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, const double* xs, const double* ys,
+                          const std::vector<uint32_t>& in_off, const std::vector<uint32_t>& out_off,
+                          const std::vector<CsEdge>& in_rec, const std::vector<CsEdge>& out_rec,
+                          const std::vector<float>& in_num, const std::vector<float>& out_num,
+                          const std::vector<float>& weight);
 
 extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_exists, const uint8_t* live,
                                      const float* weight, const double* xs, const double* ys, const double* z,
@@ -371,6 +389,7 @@ extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_ex
         rc |= upload(&g->d_ang_num, ang_num);
     }
     if (!rc) rc = build_v2_graph(g, n, node_exists, xs, ys, in_off, out_off, in_rec, out_rec, in_num, out_num, w, lv, max_deg);
+    if (!rc) rc = build_v3_graph(g, n, node_exists, xs, ys, in_off, out_off, in_rec, out_rec, in_num, out_num, w);
     if (rc) {
         delete g;
         return nullptr;
@@ -400,7 +419,9 @@ extern "C" void cs_graph_destroy(cs_graph* g) {
                     (void*)g->d_out2_num, (void*)g->d_sources2, (void*)g->d_sort_keys, (void*)g->d_sort_vals,
                     (void*)g->d_sort_vals2, (void*)g->d_fallback, (void*)g->d_fb_sources, (void*)g->d_probe,
                     (void*)g->d_src_wt2, (void*)g->d_fb_wt, (void*)g->d_eligible2, g->d_cub_tmp, (void*)g->d_scratch2,
-                    (void*)g->d_fb2_sources, (void*)g->d_fb2_wt})
+                    (void*)g->d_fb2_sources, (void*)g->d_fb2_wt, (void*)g->d3_jinfo, (void*)g->d3_links, (void*)g->d3_ctab,
+                    (void*)g->d3_cnum, (void*)g->d3_csec, (void*)g->d3_weight, (void*)g->d3_int_chain,
+                    (void*)g->d3_orig_of_new, (void*)g->d3_new_of_orig, (void*)g->d3_eligible})
         if (p) cudaFree(p);
     if (g->h_progress) cudaFreeHost(g->h_progress);
     for (auto& e : g->ev)
@@ -423,7 +444,7 @@ extern "C" int cs_graph_set_option(cs_graph* g, const char* name, double value) 
     if (!g || !name) return cs_fail("null graph or option name");
     const std::string k(name);
     if (k == "kernel") {
-        if (value != 0 && value != 1 && value != 2) return cs_fail("option kernel must be 0 (auto), 1 or 2");
+        if (value != 0 && value != 1 && value != 2 && value != 3) return cs_fail("option kernel must be 0 (auto), 1, 2 or 3");
         g->opt_kernel = (int)value;
     } else if (k == "page_bits") {
         if (value < 2 || value > 6) return cs_fail("option page_bits must be in [2, 6]");
@@ -466,19 +487,20 @@ extern "C" uint64_t cs_progress(cs_graph* g) {
 }
 
 // ------------------------------------------------------------------------------------------------ arena
-// kind 0 = shortest, 1 = segment, 2 = simplest (two states per node)
+// kind 0 = shortest, 1 = segment, 2 = simplest (two states per node), 3 = chain-contracted shortest (junction states)
 static int ensure_arena(cs_graph* g, int kind, int D) {
     if (g->d_arena && g->arena_kind == kind && g->arena_D >= D) return 0;
     if (g->d_arena) {
         CS_CUDA(cudaFree(g->d_arena));
         g->d_arena = nullptr;
     }
-    const size_t nstates = kind == 2 ? (size_t)g->n * 2 : g->n;
+    const size_t nstates = kind == 2 ? (size_t)g->n * 2 : kind == 3 ? (size_t)g->v3_J + 1 : g->n;
     uint32_t rcap = g->cfg_rcap ? g->cfg_rcap : (1u << 16);
     rcap = (uint32_t)std::min<size_t>(rcap, nstates);
     rcap = std::max(rcap, 32u);
     const uint32_t qcap = rcap * 2 + 64;
-    uint32_t workers = g->cfg_workers ? g->cfg_workers : (uint32_t)g->sm_count * CS_MIN_BLOCKS * CS_WARPS_PER_CTA;
+    uint32_t workers = g->cfg_workers ? g->cfg_workers
+                                      : (uint32_t)g->sm_count * (kind == 3 ? CS3_MIN_BLOCKS : CS_MIN_BLOCKS) * CS_WARPS_PER_CTA;
     workers = std::max<uint32_t>(CS_WARPS_PER_CTA, workers / CS_WARPS_PER_CTA * CS_WARPS_PER_CTA);
     CsArenaLayout L{};
     size_t off = 0;
@@ -576,6 +598,11 @@ static int ensure_arena_angular(cs_graph* g, int D) {
     g->arena_D = D;
     g->arena_kind = 2;
     return 0;
+}
+
+__global__ void cs_k_prep_csec(float* sec, const float* num, size_t m, float speed) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) sec[i] = __fdiv_rn(num[i], speed);
 }
 
 __global__ void cs_k_prep_seconds(CsEdge* rec, const float* num, uint64_t E, float speed) {
@@ -688,6 +715,7 @@ static int finish_call(cs_graph* g, double* out, int out_on_device, size_t elems
         stats->ctas_per_sm = g->last_v2 ? (uint32_t)g->plan.ctas_per_sm : 0;
         stats->reach_capacity = g->last_v2 ? g->plan.sm.rcap : 0;
         stats->slot_capacity = g->last_v2 ? g->plan.sm.S : 0;
+        stats->kernel_used = (uint32_t)g->last_kernel;
         cudaEventElapsedTime(&stats->kernel_ms, g->ev[1], g->ev[2]);
         cudaEventElapsedTime(&stats->total_ms, g->ev[0], g->ev[3]);
         stats->gpu_launches = launches;
@@ -732,6 +760,7 @@ static float default_delta(const cs_graph* g, float speed) {
 }
 
 #include "cs_api_v2.inl"
+#include "cs_api_v3.inl"
 
 // ------------------------------------------------------------------------------------------------ shortest
 static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
@@ -869,8 +898,96 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
     };
     const int nblk = (int)((g->n + 255) / 256);
 
+
+    // ---- chain-contracted kernel (cs_shortest3.cuh): junction-level search, chains walked in place
+    const bool dumping = dump_agg || dump_sigma || dump_npred;
+    bool use_v3 = !use_v2 && !dumping && g->v3_ok && n_sources > 0 && (g->opt_kernel == 3 || g->opt_kernel == 0);
+    if (g->opt_kernel == 3 && !use_v3 && !dumping && n_sources > 0)
+        return cs_fail("the chain-contracted kernel cannot serve this graph (an edge without a mutual twin, or a junction "
+                       "with more than %d links)", CS3_MAX_LINKS);
+    g->last_kernel = 1;
+    if (use_v3) {
+        if (ensure_arena(g, 3, D)) return 1;
+        if (g->cached_speed3 != speed && g->v3_ncsec) {
+            cs_k_prep_csec<<<(int)((g->v3_ncsec + 255) / 256), 256, 0, g->stream>>>(g->d3_csec, g->d3_cnum, g->v3_ncsec, speed);
+            launches += 1;
+            g->cached_speed3 = speed;
+        }
+        cs_k_permute_u8<<<(g->n + 255) / 256, 256, 0, g->stream>>>(g->d_eligible, g->d3_orig_of_new, g->d3_eligible, g->n);
+        launches += 1;
+        CsShortest3Params t{};
+        t.g.J = g->v3_J;
+        t.g.I = g->v3_I;
+        t.g.n = g->n;
+        t.g.jinfo = g->d3_jinfo;
+        t.g.links = g->d3_links;
+        t.g.csec = g->d3_csec;
+        t.g.ctab = g->d3_ctab;
+        t.g.int_chain = g->d3_int_chain;
+        t.g.orig_of_new = g->d3_orig_of_new;
+        t.g.new_of_orig = g->d3_new_of_orig;
+        t.g.weight = g->d3_weight;
+        t.D = D;
+        t.closeness = closeness;
+        t.betweenness = betweenness;
+        t.phase2 = p.phase2;
+        for (int i = 0; i < D; ++i) {
+            t.dist_f[i] = p.dist_f[i];
+            t.beta_f[i] = p.beta_f[i];
+            t.beta_d[i] = p.beta_d[i];
+        }
+        t.max_seconds = p.max_seconds;
+        t.speed = speed;
+        t.tol = tol;
+        t.sources = g->d_sources;
+        t.src_wt = g->d_src_wt;
+        t.n_sources = n_sources;
+        t.eligible = g->d3_eligible;
+        t.acc_c = g->d_acc;
+        t.acc_b = g->d_acc + (size_t)g->n * 5 * D;
+        t.counters = g->d_counters;
+        t.error = g->d_error;
+        t.arena = g->d_arena;
+        t.lay = g->lay;
+        t.delta = default_delta(g, speed);
+        t.bin_scale = p.bin_scale;
+        const uint32_t grid3 = (uint32_t)std::min<uint64_t>(g->workers / CS3_WARPS, (n_sources + CS3_WARPS - 1) / CS3_WARPS);
+        CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
+        const int threads3 = CS3_WARPS * 32;
+        if (D == 1) cs_k_shortest3<1><<<grid3, threads3, 0, g->stream>>>(t);
+        else if (D == 2) cs_k_shortest3<2><<<grid3, threads3, 0, g->stream>>>(t);
+        else if (D == 3) cs_k_shortest3<3><<<grid3, threads3, 0, g->stream>>>(t);
+        else if (D == 4) cs_k_shortest3<4><<<grid3, threads3, 0, g->stream>>>(t);
+        else if (D <= 8) cs_k_shortest3<8><<<grid3, threads3, 0, g->stream>>>(t);
+        else cs_k_shortest3<CS_MAX_THRESHOLDS><<<grid3, threads3, 0, g->stream>>>(t);
+        launches += 1;
+        CS_CUDA(cudaGetLastError());
+        int herr3 = 0;
+        if (g->opt_kernel == 0) {
+            // a walk that stopped increasing (a piece far below f32 resolution) is outside this kernel's contract:
+            // serve the call with the arena kernel instead
+            CS_CUDA(cudaMemcpyAsync(&herr3, g->d_error, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+            CS_CUDA(cudaStreamSynchronize(g->stream));
+        }
+        if (herr3 == CS_ERR_ZERO_TIE) {
+            CS_CUDA(cudaMemsetAsync(g->d_error, 0, sizeof(int), g->stream));
+            CS_CUDA(cudaMemsetAsync(g->d_counters, 0, CS_NCOUNTERS * sizeof(unsigned long long), g->stream));
+            CS_CUDA(cudaMemsetAsync(g->d_acc, 0, acc_elems * sizeof(double), g->stream));
+            use_v3 = false;
+        } else {
+            cs_k_epilogue_shortest3<<<nblk, 256, 0, g->stream>>>(t.acc_c, t.acc_b, d_out, g->d3_orig_of_new, g->n, D, closeness,
+                                                                 betweenness, accumulate);
+            launches += 1;
+            CS_CUDA(cudaGetLastError());
+            CS_CUDA(cudaEventRecord(g->ev[2], g->stream));
+            g->last_v2 = false;
+            g->last_kernel = 3;
+            return finish_call(g, out, out_on_device, elems, d_out, stats, launches);
+        }
+    }
     g->last_v2 = use_v2;
     g->last_fallback = 0;
+    if (use_v2) g->last_kernel = 2;
     if (use_v2) {
         q.sm = g->plan.sm;
         q.probe = 0;

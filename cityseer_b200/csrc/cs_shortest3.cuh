@@ -1,0 +1,905 @@
+// centrality_shortest, chain-contracted kernel: one warp per source, search / order / predecessors / dependencies over
+// JUNCTIONS only, chain interiors produced by walking contiguous per-chain seconds arrays (see cs_api_v3.inl for the
+// graph layout).  Same arithmetic as cs_shortest.cuh, reference /root/reference/rust/src/centrality.rs:
+//   * distances: the reference adds f32 seconds node by node (:1405); a walk over a chain performs the same additions
+//     in the same order, so every interior distance is bit-identical, and min(walk from A, walk from B) is the fixed
+//     point of the search because f32 `+` is monotone;
+//   * predecessors: an interior has one candidate predecessor (the neighbour nearer its own end) except the single
+//     last-settled node of a chain, where the two waves meet: there - and at junctions - the reference's sequential
+//     epsilon rule (:1413-1437) or tolerance rule (:1457-1482) is evaluated on the actual candidates in settle order;
+//   * sigma is constant along a one-predecessor run, and sigma_pred / sigma_succ == 1 exactly there (:861-866), so the
+//     dependency of a run is the running f64 sum of its seeds (:823-873) - evaluated in the reference's order.
+// Terminology: a LINK is one end of a chain at a junction; link j of junction v walks outward over nodes m_1 .. m_k to
+// the far junction F.  sv[t] are v's outward steps (sv[t] leads to m_{t+1}), sF[t] those of F (sF[t] leads to m_{k-t}).
+#pragma once
+#include "cs_shortest.cuh"
+
+#define CS3_KMAX 12       // interiors per chain (longer runs are cut at upload)
+#define CS3_MAX_LINKS 8   // links per junction
+#define CS3_WARPS 8
+#ifndef CS3_MIN_BLOCKS
+#define CS3_MIN_BLOCKS 2
+#endif
+#define CS3_LIST 512      // staged (node, cost) entries per warp for the packed closeness scatter
+
+struct CsV3Graph {
+    uint32_t J, I, n;
+    const uint2* jinfo;           // [J] {first link, links | in-degree << 8}
+    const uint4* links;           // {far junction, soff, ibase, k | dir << 4 | pos_at_far << 5 | canonical count << 9}
+    const float* csec;            // per chain: fwd[0..k] then bwdr[0..k] (seconds)
+    const uint4* ctab;            // per chain with interiors: {soff, ibase, k, A} {B, posA, posB, -}
+    const uint32_t* int_chain;    // [I] chain of every interior
+    const uint32_t* orig_of_new;  // [n]
+    const uint32_t* new_of_orig;  // [n]
+    const float* weight;          // [n] by new id
+};
+
+struct CsShortest3Params {
+    CsV3Graph g;
+    int D, closeness, betweenness, phase2;
+    float dist_f[CS_MAX_THRESHOLDS];
+    float beta_f[CS_MAX_THRESHOLDS];
+    double beta_d[CS_MAX_THRESHOLDS];
+    float max_seconds, speed, tol;
+    const uint32_t* sources;  // ORIGINAL indices
+    const float* src_wt;
+    unsigned long long n_sources;
+    const uint8_t* eligible;  // by new id
+    double* acc_c;            // [5 * D][n] metric-major by new id: row 5 * i + m
+    double* acc_b;            // [2 * D][n] metric-major by new id: row 2 * i (plain) / 2 * i + 1 (beta-weighted)
+    unsigned long long* counters;
+    int* error;
+    uint8_t* arena;
+    CsArenaLayout lay;        // ds sized J + 1 (slot J = a source that is an interior); linfo = per-rank link bytes
+    float delta, bin_scale;
+};
+
+struct CsView {
+    uint32_t far, sv, sF, k, id1, paf, cnt;
+    int step;
+};
+
+struct CsSrc3 {
+    uint32_t id, slot;  // new id of the source; its junction slot (J when the source is an interior)
+    uint32_t interior, soff, ibase, k, p, A, B, posA, posB;
+};
+
+__device__ __forceinline__ CsView cs3_view(const CsV3Graph& g, const CsSrc3& S, uint32_t v, uint32_t off, uint32_t j) {
+    CsView V;
+    if (v == g.J) {
+        // the source sits inside a chain at position p (1-based): two links, toward A (0) and toward B (1)
+        V.cnt = 1;
+        if (j == 0) {
+            V.sv = S.soff + (S.k + 1) + (S.k - S.p + 1);
+            V.sF = S.soff;
+            V.k = S.p - 1;
+            V.id1 = g.J + S.ibase + S.p - 2;
+            V.step = -1;
+            V.far = S.A;
+            V.paf = S.posA;
+        } else {
+            V.sv = S.soff + S.p;
+            V.sF = S.soff + (S.k + 1);
+            V.k = S.k - S.p;
+            V.id1 = g.J + S.ibase + S.p;
+            V.step = 1;
+            V.far = S.B;
+            V.paf = S.posB;
+        }
+        return V;
+    }
+    const uint4 L = __ldg(&g.links[off + j]);
+    const uint32_t k = L.w & 15u, dir = (L.w >> 4) & 1u;
+    V.far = L.x;
+    V.k = k;
+    V.paf = (L.w >> 5) & 15u;
+    V.cnt = (L.w >> 9) & 3u;
+    if (dir == 0) {
+        V.sv = L.y;
+        V.sF = L.y + k + 1;
+        V.id1 = g.J + L.z;
+        V.step = 1;
+    } else {
+        V.sv = L.y + k + 1;
+        V.sF = L.y;
+        V.id1 = g.J + L.z + k - 1;
+        V.step = -1;
+    }
+    if (S.interior && k > 0 && L.y == S.soff) {
+        // the source's own chain, seen from one of its ends: the far end is the source
+        V.far = g.J;
+        if (dir == 0) {
+            V.k = S.p - 1;
+            V.sF = L.y + (k + 1) + (k - S.p + 1);
+            V.paf = 0;
+        } else {
+            V.k = k - S.p;
+            V.sF = L.y + S.p;
+            V.paf = 1;
+        }
+    }
+    return V;
+}
+
+// settle-order tie key of a node (new id): the source first, then ascending original index
+__device__ __forceinline__ uint32_t cs3_key(const CsV3Graph& g, const CsSrc3& S, uint32_t id) {
+    return id == S.id ? 0u : __ldg(&g.orig_of_new[id]) + 1u;
+}
+// does node a (distance bits da) settle before node b?
+__device__ __forceinline__ bool cs3_before(const CsV3Graph& g, const CsSrc3& S, uint32_t da, uint32_t ida, uint32_t db, uint32_t idb) {
+    if (da != db) return da < db;
+    return cs3_key(g, S, ida) < cs3_key(g, S, idb);
+}
+
+// Two candidates reach a node: its own-side predecessor (c_own, never larger than c_oth) and the neighbour across
+// the meeting point (c_oth).  Is the latter kept as a predecessor?  Sequential rule of centrality.rs:1413-1437 in
+// arrival order, or the tolerance rule of :1457-1482 against the final distance.
+__device__ __forceinline__ bool cs3_other_kept(float c_own, float c_oth, bool own_first, bool phase2, float one_plus_tol,
+                                               float max_seconds) {
+    if (phase2) return c_oth <= __fmul_rn(c_own, one_plus_tol);
+    if (c_oth > max_seconds) return false;  // never relaxed (:1407)
+    const float one_minus = 1.0f - CS_TIE_EPS, one_plus = 1.0f + CS_TIE_EPS;
+    if (own_first) return c_oth <= __fmul_rn(c_own, one_plus);
+    // the other candidate arrived first and is replaced only by a clearly smaller one
+    if (c_own < c_oth) return !(c_own < __fmul_rn(c_oth, one_minus));
+    return true;
+}
+
+template <int DT>
+__device__ __forceinline__ int cs3_first_threshold(const CsShortest3Params& p, float cost) {
+    int ti = DT;
+#pragma unroll
+    for (int i = DT - 1; i >= 0; --i)
+        if (i < p.D && cost <= p.dist_f[i]) ti = i;
+    return ti;
+}
+
+// Closeness scatter of `total` (node, cost) pairs staged in shared memory, one lane per target (centrality.rs:1755-1777,
+// f32 terms).  The accumulators are metric-major ([5 * i + m][n] by new id): the interiors of a chain have consecutive
+// ids, so one warp-wide red.f64 covers runs of consecutive doubles.
+template <int DT>
+__device__ __forceinline__ void cs3_emit_closeness(const CsShortest3Params& p, const uint32_t* l_id, const float* l_cost,
+                                                   uint32_t total, float wt, float cycles_wt, const float* rankf,
+                                                   unsigned long long& n_ri) {
+    const uint32_t lane = cs_lane();
+    const size_t n = p.g.n;
+    for (uint32_t b0 = 0; b0 < total; b0 += 32) {
+        const uint32_t e = b0 + lane;
+        if (e < total) {
+            const uint32_t node = l_id[e];
+            const float cost = l_cost[e];
+            double* base = p.acc_c + node;
+            const double far_t = (double)__fmul_rn(cost, wt);
+            const double harm_t = (double)__fmul_rn(__fdiv_rn(1.0f, cost), wt);
+            const double wt_t = (double)wt;
+#pragma unroll
+            for (int i = 0; i < DT; ++i) {
+                if (i < p.D && cost <= p.dist_f[i]) {
+                    ++n_ri;
+                    double* q = base + (size_t)(5 * i) * n;
+                    cs_red_add(q, wt_t);
+                    cs_red_add(q + n, far_t);
+                    cs_red_add(q + 2 * n, (double)__fmul_rn(rankf[i], cycles_wt));
+                    cs_red_add(q + 3 * n, harm_t);
+                    cs_red_add(q + 4 * n, (double)__fmul_rn(expf(__fmul_rn(-p.beta_f[i], cost)), wt));
+                }
+            }
+        }
+    }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3(const CsShortest3Params p) {
+    __shared__ uint32_t s_bins_all[CS3_WARPS][CS_NBINS];  // P2 bins; afterwards the staged (node, cost) list
+    __shared__ uint32_t s_hist_all[CS3_WARPS][2][CS_MAX_THRESHOLDS + 1];
+    __shared__ float s_rank_all[CS3_WARPS][CS_MAX_THRESHOLDS];
+    __shared__ float s_walk_all[CS3_WARPS][(CS3_KMAX + 2) * 32];  // per-lane walk values, [t][lane]
+
+    const uint32_t lane = cs_lane();
+    const uint32_t ltmask = cs_lanemask_lt();
+    const uint32_t wic = threadIdx.x >> 5;
+    const uint32_t worker = blockIdx.x * CS3_WARPS + wic;
+    uint32_t* bins = s_bins_all[wic];
+    uint32_t* l_id = bins;
+    float* l_cost = reinterpret_cast<float*>(bins + CS3_LIST);
+    uint32_t* histN = s_hist_all[wic][0];
+    uint32_t* histE = s_hist_all[wic][1];
+    float* rankf = s_rank_all[wic];
+    float* walk = s_walk_all[wic];
+#define CS3_W(t) walk[(t) * 32 + lane]
+    const CsWarpArena A = cs_arena(p.arena, p.lay, worker);
+    uint8_t* linfo = A.bdone;  // [rcap][8] link bytes: T | tie2 << 4 | yhas << 5   (bdone flags live in predmask's upper half)
+    uint8_t* bdone = reinterpret_cast<uint8_t*>(A.predmask) + (size_t)A.rcap * 4;
+    const CsV3Graph& g = p.g;
+    const uint32_t J = g.J;
+    const int D = p.D;
+    const int D2 = 2 * D;
+    const float one_minus = 1.0f - CS_TIE_EPS, one_plus = 1.0f + CS_TIE_EPS;
+    const float one_plus_tol = 1.0f + p.tol;
+    const uint32_t INF = CS_INF_BITS;
+
+    for (;;) {
+        unsigned long long si = 0;
+        if (lane == 0) si = atomicAdd(&p.counters[CS_C_NEXT], 1ull);
+        si = __shfl_sync(CS_FULL, si, 0);
+        if (si >= p.n_sources) break;
+        if (*reinterpret_cast<volatile int*>(p.error) != 0) break;
+        const float wt = __ldg(&p.src_wt[si]);
+        CsSrc3 S;
+        S.id = __ldg(&g.new_of_orig[__ldg(&p.sources[si])]);
+        S.interior = S.id >= J ? 1u : 0u;
+        S.slot = S.interior ? J : S.id;
+        S.soff = S.ibase = S.k = S.p = S.A = S.B = S.posA = S.posB = 0;
+        if (S.interior) {
+            const uint32_t c = __ldg(&g.int_chain[S.id - J]);
+            const uint4 c0 = __ldg(&g.ctab[2 * c]), c1 = __ldg(&g.ctab[2 * c + 1]);
+            S.soff = c0.x;
+            S.ibase = c0.y;
+            S.k = c0.z;
+            S.A = c0.w;
+            S.B = c1.x;
+            S.posA = c1.y;
+            S.posB = c1.z;
+            S.p = S.id - J - S.ibase + 1;
+        }
+        long long tc[7];
+        tc[0] = clock64();
+
+        // ------------------------------------------------------------------ P1: junction search (label-correcting)
+        unsigned long long relax = 0, edge_iters = 0, n_interior = 0;
+        uint32_t R = 1;
+        int fail = 0;
+        {
+            uint2* qc = A.qa;
+            uint2* qn = A.qb;
+            uint2* far = A.far;
+            uint32_t nc = 1, nn = 0, nf = 0;
+            float thr = p.delta;
+            if (lane == 0) {
+                cs_st(&A.ds[S.slot], make_uint2(0u, CS_NOSLOT));
+                cs_st(&A.node_list[0], S.slot);
+                cs_st(&qc[0], make_uint2(S.slot, 0u));
+            }
+            __syncwarp();
+            for (;;) {
+                while (nc > 0) {
+                    for (uint32_t b0 = 0; b0 < nc; b0 += 32) {
+                        const uint32_t idx = b0 + lane;
+                        bool valid = idx < nc;
+                        uint32_t v = 0, abits = 0, skip = 0xffffffffu;
+                        if (valid) {
+                            const uint2 it = cs_ld(&qc[idx]);
+                            v = it.x & CS_NODE_MASK;
+                            skip = (it.x >> CS_NODE_BITS) - 1u;
+                            abits = it.y;
+                            valid = cs_ld(&A.ds[v].x) == abits;
+                        }
+                        uint32_t off = 0, deg = 0;
+                        if (valid) {
+                            if (v == J) {
+                                deg = 2;
+                            } else {
+                                const uint2 ji = __ldg(&g.jinfo[v]);
+                                off = ji.x;
+                                deg = ji.y & 0xffu;
+                            }
+                        }
+                        const uint32_t maxdeg = __reduce_max_sync(CS_FULL, deg);
+                        for (uint32_t j = 0; j < maxdeg; ++j) {
+                            bool improved = false, first = false;
+                            uint32_t nb = 0, cbits = 0, back = 0;
+                            float cand = 0.f;
+                            if (j < deg && j != skip) {
+                                const CsView V = cs3_view(g, S, v, off, j);
+                                float a = __uint_as_float(abits);
+                                bool ok = true;
+                                for (uint32_t t = 0; t <= V.k; ++t) {
+                                    a = __fadd_rn(a, __ldg(&g.csec[V.sv + t]));
+                                    if (a > p.max_seconds) {
+                                        ok = false;
+                                        break;
+                                    }
+                                }
+                                if (ok) {
+                                    nb = V.far;
+                                    cand = a;
+                                    cbits = __float_as_uint(a);
+                                    const uint32_t old = atomicMin(&A.ds[nb].x, cbits);
+                                    improved = cbits < old;
+                                    first = old == INF;
+                                    back = V.paf + 1u;
+                                }
+                            }
+                            uint32_t m = __ballot_sync(CS_FULL, first);
+                            if (m) {
+                                const uint32_t pos = R + __popc(m & ltmask);
+                                if (first && pos < A.rcap) cs_st(&A.node_list[pos], nb);
+                                R += __popc(m);
+                            }
+                            const bool pn = improved && (cand < thr);
+                            const bool pf = improved && !pn;
+                            const uint2 item = make_uint2(nb | (back << CS_NODE_BITS), cbits);
+                            m = __ballot_sync(CS_FULL, pn);
+                            if (m) {
+                                const uint32_t pos = nn + __popc(m & ltmask);
+                                if (pn && pos < A.qcap) cs_st(&qn[pos], item);
+                                nn += __popc(m);
+                            }
+                            m = __ballot_sync(CS_FULL, pf);
+                            if (m) {
+                                const uint32_t pos = nf + __popc(m & ltmask);
+                                if (pf && pos < A.qcap) cs_st(&far[pos], item);
+                                nf += __popc(m);
+                            }
+                            relax += improved ? 1ull : 0ull;
+                        }
+                    }
+                    if (R > A.rcap || nn > A.qcap || nf > A.qcap) {
+                        fail = R > A.rcap ? CS_ERR_REACH_OVERFLOW : CS_ERR_QUEUE_OVERFLOW;
+                        break;
+                    }
+                    uint2* t = qc;
+                    qc = qn;
+                    qn = t;
+                    nc = nn;
+                    nn = 0;
+                    __syncwarp();
+                }
+                if (fail || nf == 0) break;
+                float mn = __uint_as_float(INF);
+                for (uint32_t i = lane; i < nf; i += 32) {
+                    const uint2 it = cs_ld(&far[i]);
+                    if (cs_ld(&A.ds[it.x & CS_NODE_MASK].x) == it.y) mn = fminf(mn, __uint_as_float(it.y));
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(CS_FULL, mn, o));
+                if (!(mn < __uint_as_float(INF))) break;
+                thr = mn + p.delta;
+                uint32_t w = 0;
+                nc = 0;
+                for (uint32_t b0 = 0; b0 < nf; b0 += 32) {
+                    const uint32_t idx = b0 + lane;
+                    bool livee = idx < nf;
+                    uint2 it = make_uint2(0u, 0u);
+                    if (livee) {
+                        it = cs_ld(&far[idx]);
+                        livee = cs_ld(&A.ds[it.x & CS_NODE_MASK].x) == it.y;
+                    }
+                    const bool near = livee && (__uint_as_float(it.y) < thr);
+                    const bool keep = livee && !near;
+                    __syncwarp();
+                    uint32_t m = __ballot_sync(CS_FULL, near);
+                    if (near) cs_st(&qc[nc + __popc(m & ltmask)], it);
+                    nc += __popc(m);
+                    m = __ballot_sync(CS_FULL, keep);
+                    if (keep) cs_st(&far[w + __popc(m & ltmask)], it);
+                    w += __popc(m);
+                }
+                nf = w;
+                __syncwarp();
+            }
+        }
+        tc[1] = clock64();
+        if (fail) {
+            if (lane == 0) atomicCAS(p.error, 0, fail);
+            break;
+        }
+
+        // ------------------------------------------------------------------ P2: exact settle order of the junctions
+        if (lane <= CS_MAX_THRESHOLDS) {
+            histN[lane] = 0;
+            histE[lane] = 0;
+        }
+        {
+            for (uint32_t i = lane; i < CS_NBINS; i += 32) bins[i] = 0;
+            __syncwarp();
+            for (uint32_t i = lane; i < R; i += 32) {
+                const uint32_t node = cs_ld(&A.node_list[i]);
+                const uint32_t ab = cs_ld(&A.ds[node].x);
+                cs_st(reinterpret_cast<uint32_t*>(&A.s_agg[i]), ab);
+                atomicAdd(&bins[cs_bin(ab, p.bin_scale)], 1u);
+            }
+            __syncwarp();
+            {
+                uint32_t carry = 0;
+                for (uint32_t k = 0; k < CS_NBINS / 32; ++k) {
+                    const uint32_t c = bins[k * 32 + lane];
+                    uint32_t inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(CS_FULL, inc, o);
+                        if ((int)lane >= o) inc += t;
+                    }
+                    bins[k * 32 + lane] = carry + inc - c;
+                    carry += __shfl_sync(CS_FULL, inc, 31);
+                }
+            }
+            __syncwarp();
+            for (uint32_t i = lane; i < R; i += 32) {
+                const uint32_t node = cs_ld(&A.node_list[i]);
+                const uint32_t ab = cs_ld(reinterpret_cast<const uint32_t*>(&A.s_agg[i]));
+                const uint32_t pos = atomicAdd(&bins[cs_bin(ab, p.bin_scale)], 1u);
+                const uint32_t key = node == S.slot ? 0u : __ldg(&g.orig_of_new[node]) + 1u;
+                cs_st(&A.tmp_key[pos], ((unsigned long long)ab << 32) | key);
+            }
+            __syncwarp();
+            for (uint32_t pos = lane; pos < R; pos += 32) {
+                const unsigned long long key = cs_ld(&A.tmp_key[pos]);
+                const uint32_t ab = (uint32_t)(key >> 32);
+                const uint32_t bin = cs_bin(ab, p.bin_scale);
+                const uint32_t start = bin ? bins[bin - 1] : 0u;
+                const uint32_t end = bins[bin];
+                uint32_t rank = start;
+                for (uint32_t j = start; j < end; ++j) rank += (cs_ld(&A.tmp_key[j]) < key) ? 1u : 0u;
+                const uint32_t low = (uint32_t)key;
+                const uint32_t node = low ? __ldg(&g.new_of_orig[low - 1u]) : S.slot;
+                cs_st(&A.s_node[rank], node);
+                cs_st(&A.s_agg[rank], __uint_as_float(ab));
+                cs_st(&A.ds[node].y, rank);
+                cs_st(&A.sigma[rank], 0.0);
+                cs_st(&bdone[rank], (uint8_t)0);
+                edge_iters += node == J ? 2u : (__ldg(&g.jinfo[node]).y >> 8);
+            }
+            __syncwarp();
+        }
+        tc[2] = clock64();
+
+        // ------------------------------------------------------------------ P3: predecessors, sigma, chain ownership
+        for (uint32_t b0 = 0; b0 < R; b0 += 32) {
+            const uint32_t r = b0 + lane;
+            const bool valid = r < R;
+            uint32_t v = 0;
+            float cc[CS3_MAX_LINKS];
+            uint32_t cu[CS3_MAX_LINKS], cd[CS3_MAX_LINKS], crk[CS3_MAX_LINKS], cj[CS3_MAX_LINKS];
+            int ncand = 0;
+            uint32_t pmask_c = 0;
+            if (valid) {
+                v = cs_ld(&A.s_node[r]);
+                const uint32_t vid = v == J ? S.id : v;
+                const float av = cs_ld(&A.s_agg[r]);
+                const uint32_t avb = __float_as_uint(av);
+                const float cost_v = __fmul_rn(av, p.speed);
+                if (p.closeness) atomicAdd(&histN[cs3_first_threshold<DT>(p, cost_v)], 1u);
+                uint32_t off = 0, deg = 2;
+                if (v != J) {
+                    const uint2 ji = __ldg(&g.jinfo[v]);
+                    off = ji.x;
+                    deg = ji.y & 0xffu;
+                }
+                unsigned long long info8 = 0ull;
+                for (uint32_t j = 0; j < deg; ++j) {
+                    const CsView V = cs3_view(g, S, v, off, j);
+                    const uint32_t k = V.k;
+                    const uint2 dF = cs_ld(&A.ds[V.far]);
+                    const uint32_t fid = V.far == J ? S.id : V.far;
+                    // walk from F toward v: CS3_W(t) = distance of m_t via F (t = k .. 1), inf where not reached
+                    for (uint32_t t = 1; t <= k; ++t) CS3_W(t) = __uint_as_float(INF);
+                    if (dF.x != INF) {
+                        float b = __uint_as_float(dF.x);
+                        for (uint32_t t = 0; t < k; ++t) {
+                            const float nb2 = __fadd_rn(b, __ldg(&g.csec[V.sF + t]));
+                            if (nb2 > p.max_seconds) break;
+                            if (nb2 == b) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
+                            b = nb2;
+                            CS3_W(k - t) = b;
+                        }
+                    }
+                    // the neighbour on this link (m_1, or F itself) as a candidate predecessor of v
+                    const uint32_t ud = k == 0 ? dF.x : __float_as_uint(CS3_W(1));
+                    const uint32_t uid = k == 0 ? fid : V.id1;
+                    if (ud != INF && r != 0) {
+                        const bool before = k == 0 ? (dF.y < r) : cs3_before(g, S, ud, uid, avb, vid);
+                        if (before) {
+                            const float c = __fadd_rn(__uint_as_float(ud), __ldg(&g.csec[V.sF + k]));
+                            if (p.phase2 || !(c > p.max_seconds)) {
+                                // insertion by settle order of the neighbour, then its in-list position
+                                int q = ncand++;
+                                while (q > 0) {
+                                    const bool gt = cd[q - 1] != ud ? cd[q - 1] > ud
+                                                    : cu[q - 1] != uid
+                                                        ? cs3_key(g, S, cu[q - 1]) > cs3_key(g, S, uid)
+                                                        : (cj[q - 1] >> 8) > V.paf;
+                                    if (!gt) break;
+                                    cc[q] = cc[q - 1];
+                                    cu[q] = cu[q - 1];
+                                    cd[q] = cd[q - 1];
+                                    crk[q] = crk[q - 1];
+                                    cj[q] = cj[q - 1];
+                                    --q;
+                                }
+                                cc[q] = c;
+                                cu[q] = uid;
+                                cd[q] = ud;
+                                crk[q] = dF.y;  // sigma of the neighbour = sigma of F (one-predecessor run)
+                                cj[q] = j | (V.paf << 8);
+                            }
+                        }
+                    }
+                    // own side of the chain: m_1 .. m_T are reached from v first
+                    const bool wins = dF.x != INF && (dF.y > r || (dF.y == r && j < V.paf));  // ties and shared pieces
+                    uint32_t T = 0;
+                    float a = av, a_prev = av;  // a = distance of m_T (v when T == 0), a_prev that of m_{T-1}
+                    for (uint32_t t = 1; t <= k; ++t) {
+                        const float na = __fadd_rn(a, __ldg(&g.csec[V.sv + t - 1]));
+                        if (na > p.max_seconds) break;
+                        if (na == a) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
+                        const float bt = CS3_W(t);
+                        if (!(na < bt || (na == bt && (dF.x == INF || wins)))) break;
+                        a_prev = a;
+                        a = na;
+                        T = t;
+                        if (p.closeness) {
+                            const int th = cs3_first_threshold<DT>(p, __fmul_rn(na, p.speed));
+                            atomicAdd(&histN[th], 1u);
+                            atomicAdd(&histE[th], 1u);  // piece (m_{t-1}, m_t): the larger cost is m_t's
+                        }
+                    }
+                    n_interior += T;
+                    uint32_t flags = 0;
+                    // meeting pair X = m_T (v when T == 0), Y = m_{T+1} (F when T == k)
+                    const uint32_t yd = T == k ? dF.x : __float_as_uint(CS3_W(T + 1));
+                    if (yd != INF) {
+                        const float ydf = __uint_as_float(yd);
+                        if (p.closeness && V.cnt && (dF.y > r || (dF.y == r && j < V.paf))) {
+                            const float ec = __fmul_rn(fmaxf(a, ydf), p.speed);
+                            atomicAdd(&histE[cs3_first_threshold<DT>(p, ec)], V.cnt);
+                        }
+                        const uint32_t xid = T == 0 ? vid : V.id1 + V.step * (int)(T - 1);
+                        const uint32_t yid = T == k ? fid : V.id1 + V.step * (int)T;
+                        const bool x_later = cs3_before(g, S, yd, yid, __float_as_uint(a), xid);
+                        if (x_later && T >= 1) {
+                            // X has its own-side predecessor m_{T-1} and, perhaps, Y
+                            const float c_oth = __fadd_rn(ydf, __ldg(&g.csec[V.sF + (k - T)]));
+                            const uint32_t pid = T == 1 ? vid : V.id1 + V.step * (int)(T - 2);
+                            const bool own_first = cs3_before(g, S, __float_as_uint(a_prev), pid, yd, yid);
+                            if (cs3_other_kept(a, c_oth, own_first, p.phase2 != 0, one_plus_tol, p.max_seconds)) flags |= 0x10u;
+                        } else if (!x_later && T < k) {
+                            // Y (an interior on F's side) has its own predecessor m_{T+2} / F and, perhaps, X
+                            const float c_oth = __fadd_rn(a, __ldg(&g.csec[V.sv + T]));
+                            const uint32_t qd = T + 1 == k ? dF.x : __float_as_uint(CS3_W(T + 2));
+                            const uint32_t qid = T + 1 == k ? fid : V.id1 + V.step * (int)(T + 1);
+                            const bool own_first = cs3_before(g, S, qd, qid, __float_as_uint(a), xid);
+                            if (cs3_other_kept(ydf, c_oth, own_first, p.phase2 != 0, one_plus_tol, p.max_seconds)) flags |= 0x20u;
+                        }
+                    }
+                    info8 |= (unsigned long long)(T | flags) << (8 * j);
+                }
+                cs_st(reinterpret_cast<unsigned long long*>(linfo + (size_t)r * 8), info8);
+                if (ncand == 1 && !p.phase2) {
+                    pmask_c = 1u;
+                } else if (!p.phase2) {
+                    float old = __uint_as_float(INF);
+                    for (int q = 0; q < ncand; ++q) {
+                        const float c = cc[q];
+                        if (c < old) {
+                            if (c < __fmul_rn(old, one_minus)) pmask_c = 0;
+                            pmask_c |= 1u << q;
+                            old = c;
+                        } else if (c <= __fmul_rn(old, one_plus)) {
+                            bool dup = false;
+                            for (uint32_t mm = pmask_c; mm; mm &= mm - 1) dup |= cu[__ffs(mm) - 1] == cu[q];
+                            if (!dup) pmask_c |= 1u << q;
+                        }
+                    }
+                } else {
+                    const float lim = __fmul_rn(av, one_plus_tol);
+                    for (int q = 0; q < ncand; ++q) {
+                        if (cc[q] <= lim) {
+                            bool dup = false;
+                            for (uint32_t mm = pmask_c; mm; mm &= mm - 1) dup |= cu[__ffs(mm) - 1] == cu[q];
+                            if (!dup) pmask_c |= 1u << q;
+                        }
+                    }
+                }
+                uint32_t amask = 0;
+                for (uint32_t mm = pmask_c; mm; mm &= mm - 1) amask |= 1u << (cj[__ffs(mm) - 1] & 0xffu);
+                cs_st(&A.predmask[r], amask);
+                if (r == 0) cs_st(&A.sigma[r], 1.0);
+            }
+            bool pending = valid && r != 0;
+            for (;;) {
+                if (pending) {
+                    double s = 0.0;
+                    bool ok = true;
+                    for (uint32_t mm = pmask_c; mm; mm &= mm - 1) {
+                        const double sg = cs_ld(&A.sigma[crk[__ffs(mm) - 1]]);
+                        if (sg == 0.0) {
+                            ok = false;
+                            break;
+                        }
+                        s += sg;
+                    }
+                    if (ok) {
+                        if (s == 0.0) {
+                            atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);  // reached without an earlier-settled predecessor
+                            s = 1.0;
+                        }
+                        cs_st(&A.sigma[r], s);
+                        pending = false;
+                    }
+                }
+                __syncwarp();
+                if (!__any_sync(CS_FULL, pending)) break;
+            }
+        }
+        __syncwarp();
+        tc[3] = clock64();
+
+        // ------------------------------------------------------------------ P4: closeness scatter to targets
+        unsigned long long n_ri = 0, n_ci = 0;
+        if (p.closeness) {
+            if (lane < (uint32_t)D) {
+                long long ncount = 0, ecount = 0;
+                for (int t = 0; t <= (int)lane; ++t) {
+                    ncount += histN[t];
+                    ecount += histE[t];
+                }
+                rankf[lane] = ncount == 0 ? 0.0f : (float)max(ecount - ncount + 1ll, 0ll);
+                atomicAdd(&p.counters[CS_C_REACH0 + lane], (unsigned long long)(ncount > 0 ? ncount - 1 : 0));
+            }
+            __syncwarp();
+            const float cycles_wt = __fdiv_rn(wt, __ldg(&g.weight[S.id]));  // centrality.rs:1730
+            for (uint32_t b0 = 0; b0 < R; b0 += 32) {
+                const uint32_t r = b0 + lane;
+                uint32_t v = 0, off = 0, deg = 0;
+                float av = 0.f;
+                unsigned long long info8 = 0ull;
+                if (r < R) {
+                    v = cs_ld(&A.s_node[r]);
+                    av = cs_ld(&A.s_agg[r]);
+                    info8 = cs_ld(reinterpret_cast<const unsigned long long*>(linfo + (size_t)r * 8));
+                    deg = 2;
+                    if (v != J) {
+                        const uint2 ji = __ldg(&g.jinfo[v]);
+                        off = ji.x;
+                        deg = ji.y & 0xffu;
+                    }
+                }
+                // the junctions of this chunk (the source is not a target)
+                __syncwarp();
+                l_id[lane] = v;
+                l_cost[lane] = (r < R && r != 0) ? __fmul_rn(av, p.speed) : __uint_as_float(INF);
+                __syncwarp();
+                cs3_emit_closeness<DT>(p, l_id, l_cost, min(32u, R - b0), wt, cycles_wt, rankf, n_ri);
+                // their own-side interiors, link by link
+                const uint32_t maxdeg = __reduce_max_sync(CS_FULL, deg);
+                for (uint32_t j = 0; j < maxdeg; ++j) {
+                    const uint32_t T = j < deg ? (uint32_t)(info8 >> (8 * j)) & 15u : 0u;
+                    uint32_t inc = T;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(CS_FULL, inc, o);
+                        if ((int)lane >= o) inc += t;
+                    }
+                    const uint32_t total = __shfl_sync(CS_FULL, inc, 31);
+                    if (total == 0) continue;
+                    __syncwarp();
+                    if (T) {
+                        const CsView V = cs3_view(g, S, v, off, j);
+                        uint32_t pos = inc - T;
+                        float a = av;
+                        for (uint32_t t = 1; t <= T; ++t, ++pos) {
+                            a = __fadd_rn(a, __ldg(&g.csec[V.sv + t - 1]));
+                            l_id[pos] = V.id1 + V.step * (int)(t - 1);
+                            l_cost[pos] = __fmul_rn(a, p.speed);
+                        }
+                    }
+                    __syncwarp();
+                    cs3_emit_closeness<DT>(p, l_id, l_cost, total, wt, cycles_wt, rankf, n_ri);
+                }
+            }
+        }
+        __syncwarp();
+        tc[4] = clock64();
+
+        // ------------------------------------------------------------------ P5: dependencies, reverse settle order
+        if (p.betweenness) {
+            const double wt_d = (double)wt;
+            for (int b0 = (int)((R - 1) & ~31u); b0 >= 0; b0 -= 32) {
+                const uint32_t r = (uint32_t)b0 + lane;
+                const bool valid = r < R;
+                uint32_t w = 0, off = 0, deg = 0;
+                uint32_t frk[CS3_MAX_LINKS];  // rank of F where F depends on this junction through link j
+                uint32_t need = 0, same_chunk = 0;
+                double sigma_w = 1.0;
+                float aw = 0.f;
+                unsigned long long info8 = 0ull;
+                if (valid) {
+                    w = cs_ld(&A.s_node[r]);
+                    aw = cs_ld(&A.s_agg[r]);
+                    sigma_w = cs_ld(&A.sigma[r]);
+                    info8 = cs_ld(reinterpret_cast<const unsigned long long*>(linfo + (size_t)r * 8));
+                    deg = 2;
+                    if (w != J) {
+                        const uint2 ji = __ldg(&g.jinfo[w]);
+                        off = ji.x;
+                        deg = ji.y & 0xffu;
+                    }
+                    for (uint32_t j = 0; j < deg; ++j) {
+                        const CsView V = cs3_view(g, S, w, off, j);
+                        const uint32_t T = (uint32_t)(info8 >> (8 * j)) & 15u;
+                        frk[j] = CS_NOSLOT;
+                        if (T != V.k) continue;
+                        const uint2 dF = cs_ld(&A.ds[V.far]);
+                        if (dF.x == INF || dF.y <= r) continue;
+                        if ((cs_ld(&A.predmask[dF.y]) >> V.paf) & 1u) {
+                            frk[j] = dF.y;
+                            need |= 1u << j;
+                            if (dF.y < (uint32_t)b0 + 32u) same_chunk |= 1u << j;
+                        }
+                    }
+                }
+                bool pending = valid;
+                for (;;) {
+                    if (pending) {
+                        bool ok = true;
+                        for (uint32_t mm = same_chunk; mm; mm &= mm - 1) ok = ok && (cs_ld(&bdone[frk[__ffs(mm) - 1]]) != 0);
+                        if (ok) {
+                            double acc[DT], accb[DT];
+#pragma unroll
+                            for (int i = 0; i < DT; ++i) acc[i] = accb[i] = 0.0;
+                            for (uint32_t j = 0; j < deg; ++j) {
+                                const uint32_t ib = (uint32_t)(info8 >> (8 * j)) & 0xffu;
+                                const uint32_t T = ib & 15u;
+                                const bool tie2 = (ib & 0x10u) != 0, yhas = (ib & 0x20u) != 0;
+                                const bool needF = (need >> j) & 1u;
+                                if (T == 0 && !needF && !yhas) continue;
+                                const CsView V = cs3_view(g, S, w, off, j);
+                                const uint32_t k = V.k;
+                                double dl[DT], dlb[DT];  // dependency flowing toward this junction along the link
+#pragma unroll
+                                for (int i = 0; i < DT; ++i) dl[i] = dlb[i] = 0.0;
+                                double sigma_F = 0.0;
+                                if (needF || yhas || tie2) sigma_F = cs_ld(&A.sigma[cs_ld(&A.ds[V.far].y)]);
+                                if (needF) {
+                                    // the whole chain is on this side and F continues the path (centrality.rs:861-866)
+                                    const double f = (sigma_F == sigma_w) ? 1.0 : sigma_w / sigma_F;
+                                    const double* dx = A.dep + (size_t)frk[j] * D2;
+#pragma unroll
+                                    for (int i = 0; i < DT; ++i) {
+                                        if (i < D) {
+                                            dl[i] = f * cs_ld(&dx[i]);
+                                            dlb[i] = f * cs_ld(&dx[D + i]);
+                                        }
+                                    }
+                                } else if (yhas) {
+                                    // Y = m_{T+1} was reached from F but keeps m_T (or this junction) as a second
+                                    // predecessor: it is the last-settled node of the chain, so its dependency is its seed
+                                    float b = __uint_as_float(cs_ld(&A.ds[V.far].x));
+                                    for (uint32_t t = 0; t < k - T; ++t) b = __fadd_rn(b, __ldg(&g.csec[V.sF + t]));
+                                    const float cost_y = __fmul_rn(b, p.speed);
+                                    const uint32_t yid = V.id1 + V.step * (int)T;
+                                    const double pc = __ldg(&p.eligible[yid]) ? 0.5 : 1.0;
+                                    const double f = sigma_w / (sigma_F + sigma_w);
+#pragma unroll
+                                    for (int i = 0; i < DT; ++i) {
+                                        if (i < D && cost_y <= p.dist_f[i]) {
+                                            dl[i] = f * pc;
+                                            dlb[i] = f * (pc * exp(-p.beta_d[i] * (double)cost_y));
+                                        }
+                                    }
+                                }
+                                if (T) {
+                                    float a = aw;
+                                    for (uint32_t t = 1; t <= T; ++t) {
+                                        a = __fadd_rn(a, __ldg(&g.csec[V.sv + t - 1]));
+                                        CS3_W(t) = a;
+                                    }
+                                    for (uint32_t t = T; t >= 1; --t) {
+                                        const float cost_t = __fmul_rn(CS3_W(t), p.speed);
+                                        const uint32_t id = V.id1 + V.step * (int)(t - 1);
+                                        const double pc = __ldg(&p.eligible[id]) ? 0.5 : 1.0;
+                                        // m_T with two predecessors has sigma_w + sigma_F paths (the source never sits here)
+                                        const double f = (t == T && tie2) ? sigma_w / (sigma_w + sigma_F) : 1.0;
+                                        double* row = p.acc_b + id;
+#pragma unroll
+                                        for (int i = 0; i < DT; ++i) {
+                                            if (i < D) {
+                                                double seed = 0.0, seedb = 0.0;
+                                                if (cost_t <= p.dist_f[i]) {
+                                                    seed = pc;
+                                                    seedb = pc * exp(-p.beta_d[i] * (double)cost_t);
+                                                }
+                                                const double dpn = seed + dl[i], dpb = seedb + dlb[i];
+                                                const double credit = dpn - seed, creditb = dpb - seedb;
+                                                if (credit > 0.0 || creditb > 0.0) {
+                                                    ++n_ci;
+                                                    if (credit > 0.0) cs_red_add(row + (size_t)(2 * i) * g.n, credit * wt_d);
+                                                    if (creditb > 0.0) cs_red_add(row + (size_t)(2 * i + 1) * g.n, creditb * wt_d);
+                                                }
+                                                dl[i] = f * dpn;
+                                                dlb[i] = f * dpb;
+                                            }
+                                        }
+                                    }
+                                }
+#pragma unroll
+                                for (int i = 0; i < DT; ++i) {
+                                    acc[i] += dl[i];
+                                    accb[i] += dlb[i];
+                                }
+                            }
+                            const bool is_src = r == 0;
+                            const uint32_t wid = w == J ? S.id : w;
+                            const float cost_w = __fmul_rn(aw, p.speed);
+                            const double pc = is_src ? 0.0 : (__ldg(&p.eligible[wid]) ? 0.5 : 1.0);
+                            double* dr = A.dep + (size_t)r * D2;
+                            double* row = p.acc_b + wid;
+#pragma unroll
+                            for (int i = 0; i < DT; ++i) {
+                                if (i < D) {
+                                    double seed = 0.0, seedb = 0.0;
+                                    if (!is_src && cost_w <= p.dist_f[i]) {
+                                        seed = pc;
+                                        seedb = pc * exp(-p.beta_d[i] * (double)cost_w);
+                                    }
+                                    const double dpn = seed + acc[i], dpb = seedb + accb[i];
+                                    cs_st(&dr[i], dpn);
+                                    cs_st(&dr[D + i], dpb);
+                                    if (!is_src) {
+                                        const double credit = dpn - seed, creditb = dpb - seedb;
+                                        if (credit > 0.0 || creditb > 0.0) {
+                                            ++n_ci;
+                                            if (credit > 0.0) cs_red_add(row + (size_t)(2 * i) * g.n, credit * wt_d);
+                                            if (creditb > 0.0) cs_red_add(row + (size_t)(2 * i + 1) * g.n, creditb * wt_d);
+                                        }
+                                    }
+                                }
+                            }
+                            __threadfence_block();
+                            cs_st(&bdone[r], (uint8_t)1);
+                            pending = false;
+                        }
+                    }
+                    __syncwarp();
+                    if (!__any_sync(CS_FULL, pending)) break;
+                }
+            }
+        }
+        tc[5] = clock64();
+
+        // ------------------------------------------------------------------ P6: reset the dense map
+        cs_p6_reset(A, R);
+        tc[6] = clock64();
+
+        edge_iters = cs_warp_sum(edge_iters);
+        relax = cs_warp_sum(relax);
+        n_ri = cs_warp_sum(n_ri);
+        n_ci = cs_warp_sum(n_ci);
+        n_interior = cs_warp_sum(n_interior);
+        if (lane == 0) {
+            atomicAdd(&p.counters[CS_C_SOURCES], 1ull);
+            atomicAdd(&p.counters[CS_C_SETTLED], (unsigned long long)R + n_interior);
+            atomicAdd(&p.counters[CS_C_EDGE_ITERS], edge_iters + 2ull * n_interior);
+            atomicAdd(&p.counters[CS_C_RELAX], relax);
+            if (n_ri) atomicAdd(&p.counters[CS_C_SUM_RI], n_ri);
+            if (n_ci) atomicAdd(&p.counters[CS_C_SUM_CI], n_ci);
+            atomicAdd(&p.counters[CS_C_PROGRESS], 1ull);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) atomicAdd(&p.counters[CS_C_PHASE0 + k], (unsigned long long)(tc[k + 1] - tc[k]));
+        }
+    }
+#undef CS3_W
+}
+
+// Epilogue for the metric-major accumulators of the chain-contracted kernel: new-id columns -> [7][D][node_bound] in
+// original index order.
+__global__ void cs_k_epilogue_shortest3(const double* __restrict__ acc_c, const double* __restrict__ acc_b, double* out,
+                                        const uint32_t* __restrict__ orig_of_new, uint32_t n, int D, int closeness,
+                                        int betweenness, int add) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t node = orig_of_new[v];
+    for (int i = 0; i < D; ++i) {
+        for (int m = 0; m < 5; ++m) {
+            double* o = out + ((size_t)(m * D + i)) * n + node;
+            const double val = closeness ? acc_c[(size_t)(5 * i + m) * n + v] : 0.0;
+            if (closeness || !add) *o = add ? *o + val : val;
+        }
+        for (int b = 0; b < 2; ++b) {
+            double* o = out + ((size_t)((5 + b) * D + i)) * n + node;
+            const double val = betweenness ? acc_b[(size_t)(2 * i + b) * n + v] : 0.0;
+            if (betweenness || !add) *o = add ? *o + val : val;
+        }
+    }
+}

@@ -44,6 +44,8 @@ typedef struct cs_stats {
     uint32_t ctas_per_sm;     /* shared-memory kernel: resident CTAs per SM */
     uint32_t reach_capacity;  /* shared-memory kernel: reached nodes per source it can hold */
     uint32_t slot_capacity;   /* shared-memory kernel: distance-map slots (pages x page size) */
+    uint32_t kernel_used;     /* centrality_shortest: 1 global-arena kernel, 2 shared-memory kernel, 3 chain-contracted kernel */
+    uint32_t reserved;
 } cs_stats;
 
 const char* cs_last_error(void);
@@ -70,8 +72,9 @@ void cs_graph_destroy(cs_graph* g);
  * resident warps.  */
 int cs_graph_configure(cs_graph* g, uint32_t reach_capacity, float delta_seconds, uint32_t workers);
 
-/* Named tunables of the search kernels: "kernel" (0 = choose per call, 1 = global-arena kernel only, 2 = require the
- * shared-memory kernel), "page_bits" (log2 nodes per shared-memory page, default 4), "delta_factor" (near/far bucket
+/* Named tunables of the search kernels: "kernel" (0 = choose per call: the chain-contracted kernel when the graph
+ * qualifies, else the global-arena kernel; 1 = global-arena kernel only; 2 = require the shared-memory kernel;
+ * 3 = require the chain-contracted kernel), "page_bits" (log2 nodes per shared-memory page, default 4), "delta_factor" (near/far bucket
  * width in mean edge traversal times, default 6). */
 int cs_graph_set_option(cs_graph* g, const char* name, double value);
 

@@ -37,8 +37,8 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_stats_struct_layout_matches_header():
-    # cs_stats: 6 x u64 + 16 x u64 + 2 x f32 + 2 x u32 + 8 x u64 (phase cycles) + u64 (fallback sources) + 4 x u32 (layout)
-    assert ctypes.sizeof(_native.CsStats) == 6 * 8 + 16 * 8 + 2 * 4 + 2 * 4 + 8 * 8 + 8 + 4 * 4
+    # cs_stats: 6 x u64 + 16 x u64 + 2 x f32 + 2 x u32 + 8 x u64 (phase cycles) + u64 (fallback sources) + 6 x u32 (layout, kernel)
+    assert ctypes.sizeof(_native.CsStats) == 6 * 8 + 16 * 8 + 2 * 4 + 2 * 4 + 8 * 8 + 8 + 6 * 4
     text = open(os.path.join(ROOT, "include", "cityseer_b200.h")).read()
     assert "#define CS_MAX_THRESHOLDS 16" in text and _native.MAX_THRESHOLDS == 16
 

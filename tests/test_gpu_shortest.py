@@ -14,10 +14,10 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # stated tolerance for floating-point metrics
 
 
-@pytest.fixture(autouse=True, params=[2, 1], ids=["smem-kernel", "arena-kernel"])
+@pytest.fixture(autouse=True, params=[3, 2, 1], ids=["chain-kernel", "smem-kernel", "arena-kernel"])
 def kernel_choice(request):
-    """Every test runs against both search kernels: 2 = shared-memory CTA-per-source kernel (required, no silent
-    fallback), 1 = global-arena warp-per-source kernel."""
+    """Every test runs against all three search kernels: 3 = chain-contracted warp-per-source kernel and 2 = shared-memory
+    CTA-per-source kernel (both required, no silent fallback), 1 = global-arena warp-per-source kernel."""
     from cityseer_b200 import _native
 
     _native.DEFAULT_OPTIONS["kernel"] = float(request.param)
