@@ -762,6 +762,25 @@ static float default_delta(const cs_graph* g, float speed) {
 #include "cs_api_v2.inl"
 #include "cs_api_v3.inl"
 
+template <int DT>
+static cudaError_t v3_launch_t(const CsShortest3Params& t, uint32_t grid, int threads, cudaStream_t st) {
+    constexpr uint32_t smem = cs3_smem_bytes<DT>();
+    cudaError_t e = cudaFuncSetAttribute(cs_k_shortest3<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cs_k_shortest3<DT><<<grid, threads, smem, st>>>(t);
+    return cudaGetLastError();
+}
+static cudaError_t v3_launch(const CsShortest3Params& t, uint32_t grid, int threads, cudaStream_t st) {
+    switch (cs_shortest_dt(t.D)) {
+        case 1: return v3_launch_t<1>(t, grid, threads, st);
+        case 2: return v3_launch_t<2>(t, grid, threads, st);
+        case 3: return v3_launch_t<3>(t, grid, threads, st);
+        case 4: return v3_launch_t<4>(t, grid, threads, st);
+        case 8: return v3_launch_t<8>(t, grid, threads, st);
+        default: return v3_launch_t<CS_MAX_THRESHOLDS>(t, grid, threads, st);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ shortest
 static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
                         float speed, float tol, int closeness, int betweenness, uint64_t n_sources,
@@ -954,12 +973,7 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
         const uint32_t grid3 = (uint32_t)std::min<uint64_t>(g->workers / CS3_WARPS, (n_sources + CS3_WARPS - 1) / CS3_WARPS);
         CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
         const int threads3 = CS3_WARPS * 32;
-        if (D == 1) cs_k_shortest3<1><<<grid3, threads3, 0, g->stream>>>(t);
-        else if (D == 2) cs_k_shortest3<2><<<grid3, threads3, 0, g->stream>>>(t);
-        else if (D == 3) cs_k_shortest3<3><<<grid3, threads3, 0, g->stream>>>(t);
-        else if (D == 4) cs_k_shortest3<4><<<grid3, threads3, 0, g->stream>>>(t);
-        else if (D <= 8) cs_k_shortest3<8><<<grid3, threads3, 0, g->stream>>>(t);
-        else cs_k_shortest3<CS_MAX_THRESHOLDS><<<grid3, threads3, 0, g->stream>>>(t);
+        CS_CUDA(v3_launch(t, grid3, threads3, g->stream));
         launches += 1;
         CS_CUDA(cudaGetLastError());
         int herr3 = 0;

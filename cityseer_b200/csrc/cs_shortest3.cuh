@@ -20,6 +20,9 @@
 #ifndef CS3_MIN_BLOCKS
 #define CS3_MIN_BLOCKS 2
 #endif
+#ifndef CS3_PHASE_SYNC
+#define CS3_PHASE_SYNC 1
+#endif
 #define CS3_LIST 512      // staged (node, cost) entries per warp for the packed closeness scatter
 
 struct CsV3Graph {
@@ -145,6 +148,10 @@ __device__ __forceinline__ bool cs3_other_kept(float c_own, float c_oth, bool ow
     return true;
 }
 
+// one copy of the f64 exponential (the beta-weighted seeds, centrality.rs:1805) instead of one per call site and
+// threshold: the dependency phase has to stay inside the instruction cache
+__device__ __noinline__ double cs3_exp(double x) { return exp(x); }
+
 template <int DT>
 __device__ __forceinline__ int cs3_first_threshold(const CsShortest3Params& p, float cost) {
     int ti = DT;
@@ -190,26 +197,45 @@ __device__ __forceinline__ void cs3_emit_closeness(const CsShortest3Params& p, c
 
 template <int DT>
 __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3(const CsShortest3Params p) {
-    __shared__ uint32_t s_bins_all[CS3_WARPS][CS_NBINS];  // P2 bins; afterwards the staged (node, cost) list
+    // per-warp shared memory: region A (4 KB): P2 bins | P3 candidates | P4 staged (node, cost) list | P5 node ids / costs;
+    // region B (6 KB): P3 walk values | P5 per-node seeds -> credits; region C: P3 / P5 link list, link bytes, P5 outflow
+    constexpr uint32_t NB = DT <= 3 ? 128u : DT == 4 ? 96u : 24u;  // staged nodes per P5 sub-iteration
+    constexpr uint32_t BYTES_A = CS_NBINS * 4, BYTES_B = 2 * DT * NB * 8;
+    constexpr uint32_t BYTES_C = 2 * DT * 32 * 8 + 256 * 2 + 256;
+    constexpr uint32_t BYTES_W = BYTES_A + BYTES_B + BYTES_C;
+    static_assert(BYTES_B >= (CS3_KMAX + 2) * 32 * 4, "walk values must fit region B");
+    static_assert(3 * NB * 4 <= BYTES_A && NB >= CS3_KMAX, "P5 node staging must fit region A");
+    extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ uint32_t s_hist_all[CS3_WARPS][2][CS_MAX_THRESHOLDS + 1];
     __shared__ float s_rank_all[CS3_WARPS][CS_MAX_THRESHOLDS];
-    __shared__ float s_walk_all[CS3_WARPS][(CS3_KMAX + 2) * 32];  // per-lane walk values, [t][lane]
 
     const uint32_t lane = cs_lane();
     const uint32_t ltmask = cs_lanemask_lt();
     const uint32_t wic = threadIdx.x >> 5;
     const uint32_t worker = blockIdx.x * CS3_WARPS + wic;
-    uint32_t* bins = s_bins_all[wic];
+    uint8_t* s_warp = s_dyn + (size_t)wic * BYTES_W;
+    uint32_t* bins = reinterpret_cast<uint32_t*>(s_warp);
     uint32_t* l_id = bins;
     float* l_cost = reinterpret_cast<float*>(bins + CS3_LIST);
+    float* s_cc = reinterpret_cast<float*>(bins);  // P3 candidates [32 junctions][8 links]
+    uint32_t* s_cd = bins + 256;
+    uint32_t* s_cu = bins + 512;
+    uint32_t* s_cr = bins + 768;
+    uint32_t* s_ids = bins;                        // P5 staged nodes
+    float* s_cst = reinterpret_cast<float*>(bins + NB);
+    float* s_pcs = reinterpret_cast<float*>(bins + 2 * NB);
+    float* walk = reinterpret_cast<float*>(s_warp + BYTES_A);
+    double* s_crd = reinterpret_cast<double*>(s_warp + BYTES_A);
+    double* s_acc = reinterpret_cast<double*>(s_warp + BYTES_A + BYTES_B);
+    uint16_t* s_llist = reinterpret_cast<uint16_t*>(s_warp + BYTES_A + BYTES_B + 2 * DT * 32 * 8);
+    uint8_t* s_info = s_warp + BYTES_A + BYTES_B + 2 * DT * 32 * 8 + 512;
     uint32_t* histN = s_hist_all[wic][0];
     uint32_t* histE = s_hist_all[wic][1];
     float* rankf = s_rank_all[wic];
-    float* walk = s_walk_all[wic];
 #define CS3_W(t) walk[(t) * 32 + lane]
     const CsWarpArena A = cs_arena(p.arena, p.lay, worker);
-    uint8_t* linfo = A.bdone;  // [rcap][8] link bytes: T | tie2 << 4 | yhas << 5   (bdone flags live in predmask's upper half)
-    uint8_t* bdone = reinterpret_cast<uint8_t*>(A.predmask) + (size_t)A.rcap * 4;
+    uint8_t* linfo = A.bdone;          // [rcap][8] link bytes: T | tie2 << 4 | yhas << 5
+    uint32_t* minsucc = A.node_list;   // [rcap] after P2: smallest rank that has this junction as a predecessor
     const CsV3Graph& g = p.g;
     const uint32_t J = g.J;
     const int D = p.D;
@@ -218,15 +244,35 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
     const float one_plus_tol = 1.0f + p.tol;
     const uint32_t INF = CS_INF_BITS;
 
+    // The warps of a CTA take CS3_WARPS consecutive sources and move through the phases together (one barrier per
+    // phase): the kernel is far larger than the 32 KB instruction cache level next to the SM, and sixteen warps in
+    // sixteen different phases starve on instruction fetch (profiles/r01l: no_instruction was the top stall).
+    __shared__ unsigned long long s_base;
+    __shared__ int s_err;
     for (;;) {
+#if CS3_PHASE_SYNC
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_base = atomicAdd(&p.counters[CS_C_NEXT], (unsigned long long)CS3_WARPS);
+            s_err = *reinterpret_cast<volatile int*>(p.error);
+        }
+        __syncthreads();
+        if (s_base >= p.n_sources || s_err != 0) break;
+        const unsigned long long si = s_base + wic;
+        bool run = si < p.n_sources;
+#define CS3_BAR() __syncthreads()
+#else
         unsigned long long si = 0;
         if (lane == 0) si = atomicAdd(&p.counters[CS_C_NEXT], 1ull);
         si = __shfl_sync(CS_FULL, si, 0);
         if (si >= p.n_sources) break;
         if (*reinterpret_cast<volatile int*>(p.error) != 0) break;
-        const float wt = __ldg(&p.src_wt[si]);
+        bool run = true;
+#define CS3_BAR()
+#endif
+        const float wt = run ? __ldg(&p.src_wt[si]) : 0.f;
         CsSrc3 S;
-        S.id = __ldg(&g.new_of_orig[__ldg(&p.sources[si])]);
+        S.id = run ? __ldg(&g.new_of_orig[__ldg(&p.sources[si])]) : 0u;
         S.interior = S.id >= J ? 1u : 0u;
         S.slot = S.interior ? J : S.id;
         S.soff = S.ibase = S.k = S.p = S.A = S.B = S.posA = S.posB = 0;
@@ -249,7 +295,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
         unsigned long long relax = 0, edge_iters = 0, n_interior = 0;
         uint32_t R = 1;
         int fail = 0;
-        {
+        if (run) {
             uint2* qc = A.qa;
             uint2* qn = A.qb;
             uint2* far = A.far;
@@ -382,15 +428,21 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
         tc[1] = clock64();
         if (fail) {
             if (lane == 0) atomicCAS(p.error, 0, fail);
+#if CS3_PHASE_SYNC
+            run = false;
+#else
             break;
+#endif
         }
+        if (!run) R = 0;  // an idle warp still meets the barriers; every loop below is empty for it
+        CS3_BAR();
 
         // ------------------------------------------------------------------ P2: exact settle order of the junctions
         if (lane <= CS_MAX_THRESHOLDS) {
             histN[lane] = 0;
             histE[lane] = 0;
         }
-        {
+        if (run) {
             for (uint32_t i = lane; i < CS_NBINS; i += 32) bins[i] = 0;
             __syncwarp();
             for (uint32_t i = lane; i < R; i += 32) {
@@ -437,132 +489,171 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 cs_st(&A.s_agg[rank], __uint_as_float(ab));
                 cs_st(&A.ds[node].y, rank);
                 cs_st(&A.sigma[rank], 0.0);
-                cs_st(&bdone[rank], (uint8_t)0);
+                cs_st(&minsucc[rank], CS_NOSLOT);  // (node_list is dead from here on)
                 edge_iters += node == J ? 2u : (__ldg(&g.jinfo[node]).y >> 8);
             }
             __syncwarp();
         }
         tc[2] = clock64();
+        CS3_BAR();
 
         // ------------------------------------------------------------------ P3: predecessors, sigma, chain ownership
+        // P3a, one lane per LINK of the chunk's junctions: walk the chain from both ends, decide which interiors belong
+        // to this end, evaluate the meeting pair, and leave the link's candidate predecessor of the junction in shared
+        // memory.  P3b, one lane per junction: the reference's sequential rule over its candidates, then sigma.
         for (uint32_t b0 = 0; b0 < R; b0 += 32) {
             const uint32_t r = b0 + lane;
             const bool valid = r < R;
-            uint32_t v = 0;
-            float cc[CS3_MAX_LINKS];
-            uint32_t cu[CS3_MAX_LINKS], cd[CS3_MAX_LINKS], crk[CS3_MAX_LINKS], cj[CS3_MAX_LINKS];
-            int ncand = 0;
-            uint32_t pmask_c = 0;
+            uint32_t v = 0, off = 0, deg = 0, vid = 0, avb = 0;
             if (valid) {
                 v = cs_ld(&A.s_node[r]);
-                const uint32_t vid = v == J ? S.id : v;
-                const float av = cs_ld(&A.s_agg[r]);
-                const uint32_t avb = __float_as_uint(av);
-                const float cost_v = __fmul_rn(av, p.speed);
-                if (p.closeness) atomicAdd(&histN[cs3_first_threshold<DT>(p, cost_v)], 1u);
-                uint32_t off = 0, deg = 2;
+                vid = v == J ? S.id : v;
+                avb = __float_as_uint(cs_ld(&A.s_agg[r]));
+                if (p.closeness) atomicAdd(&histN[cs3_first_threshold<DT>(p, __fmul_rn(__uint_as_float(avb), p.speed))], 1u);
+                deg = 2;
                 if (v != J) {
                     const uint2 ji = __ldg(&g.jinfo[v]);
                     off = ji.x;
                     deg = ji.y & 0xffu;
                 }
+            }
+            uint32_t inc = deg;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(CS_FULL, inc, o);
+                if ((int)lane >= o) inc += t;
+            }
+            const uint32_t totalL = __shfl_sync(CS_FULL, inc, 31);
+            __syncwarp();
+            for (uint32_t j = 0; j < deg; ++j) s_llist[inc - deg + j] = (uint16_t)(lane | (j << 5));
+            __syncwarp();
+            for (uint32_t base = 0; base < totalL; base += 32) {
+                const uint32_t e = base + lane;
+                const bool act = e < totalL;
+                const uint32_t code = act ? s_llist[e] : 0u;
+                const uint32_t jl = code & 31u, j = code >> 5;
+                const uint32_t lv = __shfl_sync(CS_FULL, v, jl), loff = __shfl_sync(CS_FULL, off, jl);
+                const uint32_t lvid = __shfl_sync(CS_FULL, vid, jl), lavb = __shfl_sync(CS_FULL, avb, jl);
+                if (!act) continue;
+                const uint32_t lr = b0 + jl;
+                const float av = __uint_as_float(lavb);
+                const CsView V = cs3_view(g, S, lv, loff, j);
+                const uint32_t k = V.k;
+                const uint2 dF = cs_ld(&A.ds[V.far]);
+                const uint32_t fid = V.far == J ? S.id : V.far;
+                // walk from F toward v: CS3_W(t) = distance of m_t via F (t = k .. 1), inf where not reached
+                for (uint32_t t = 1; t <= k; ++t) CS3_W(t) = __uint_as_float(INF);
+                if (dF.x != INF) {
+                    float b = __uint_as_float(dF.x);
+                    for (uint32_t t = 0; t < k; ++t) {
+                        const float nb2 = __fadd_rn(b, __ldg(&g.csec[V.sF + t]));
+                        if (nb2 > p.max_seconds) break;
+                        if (nb2 == b) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
+                        b = nb2;
+                        CS3_W(k - t) = b;
+                    }
+                }
+                // the neighbour on this link (m_1, or F itself) as a candidate predecessor of v
+                const uint32_t ud = k == 0 ? dF.x : __float_as_uint(CS3_W(1));
+                const uint32_t uid = k == 0 ? fid : V.id1;
+                uint32_t c_ud = INF;
+                float c_c = 0.f;
+                if (ud != INF && lr != 0) {
+                    const bool before = k == 0 ? (dF.y < lr) : cs3_before(g, S, ud, uid, lavb, lvid);
+                    if (before) {
+                        const float c = __fadd_rn(__uint_as_float(ud), __ldg(&g.csec[V.sF + k]));
+                        if (p.phase2 || !(c > p.max_seconds)) {
+                            c_ud = ud;
+                            c_c = c;
+                        }
+                    }
+                }
+                s_cc[jl * 8 + j] = c_c;
+                s_cd[jl * 8 + j] = c_ud;
+                s_cu[jl * 8 + j] = uid | (V.paf << 28);
+                s_cr[jl * 8 + j] = dF.y;  // sigma of the neighbour = sigma of F (one-predecessor run)
+                // own side of the chain: m_1 .. m_T are reached from v first
+                const bool wins = dF.x == INF || dF.y > lr || (dF.y == lr && j < V.paf);  // exact ties, shared pieces
+                uint32_t T = 0;
+                float a = av, a_prev = av;  // a = distance of m_T (v when T == 0), a_prev that of m_{T-1}
+                for (uint32_t t = 1; t <= k; ++t) {
+                    const float na = __fadd_rn(a, __ldg(&g.csec[V.sv + t - 1]));
+                    if (na > p.max_seconds) break;
+                    if (na == a) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
+                    const float bt = CS3_W(t);
+                    if (!(na < bt || (na == bt && wins))) break;
+                    a_prev = a;
+                    a = na;
+                    T = t;
+                    if (p.closeness) {
+                        const int th = cs3_first_threshold<DT>(p, __fmul_rn(na, p.speed));
+                        atomicAdd(&histN[th], 1u);
+                        atomicAdd(&histE[th], 1u);  // piece (m_{t-1}, m_t): the larger cost is m_t's
+                    }
+                }
+                n_interior += T;
+                uint32_t flags = 0;
+                // meeting pair X = m_T (v when T == 0), Y = m_{T+1} (F when T == k)
+                const uint32_t yd = T == k ? dF.x : __float_as_uint(CS3_W(T + 1));
+                if (yd != INF) {
+                    const float ydf = __uint_as_float(yd);
+                    if (p.closeness && V.cnt && (dF.y > lr || (dF.y == lr && j < V.paf))) {
+                        const float ec = __fmul_rn(fmaxf(a, ydf), p.speed);
+                        atomicAdd(&histE[cs3_first_threshold<DT>(p, ec)], V.cnt);
+                    }
+                    const uint32_t xid = T == 0 ? lvid : V.id1 + V.step * (int)(T - 1);
+                    const uint32_t yid = T == k ? fid : V.id1 + V.step * (int)T;
+                    const bool x_later = cs3_before(g, S, yd, yid, __float_as_uint(a), xid);
+                    if (x_later && T >= 1) {
+                        // X has its own-side predecessor m_{T-1} and, perhaps, Y
+                        const float c_oth = __fadd_rn(ydf, __ldg(&g.csec[V.sF + (k - T)]));
+                        const uint32_t pid = T == 1 ? lvid : V.id1 + V.step * (int)(T - 2);
+                        const bool own_first = cs3_before(g, S, __float_as_uint(a_prev), pid, yd, yid);
+                        if (cs3_other_kept(a, c_oth, own_first, p.phase2 != 0, one_plus_tol, p.max_seconds)) flags |= 0x10u;
+                    } else if (!x_later && T < k) {
+                        // Y (an interior on F's side) has its own predecessor m_{T+2} / F and, perhaps, X
+                        const float c_oth = __fadd_rn(a, __ldg(&g.csec[V.sv + T]));
+                        const uint32_t qd = T + 1 == k ? dF.x : __float_as_uint(CS3_W(T + 2));
+                        const uint32_t qid = T + 1 == k ? fid : V.id1 + V.step * (int)(T + 1);
+                        const bool own_first = cs3_before(g, S, qd, qid, __float_as_uint(a), xid);
+                        if (cs3_other_kept(ydf, c_oth, own_first, p.phase2 != 0, one_plus_tol, p.max_seconds)) flags |= 0x20u;
+                    }
+                }
+                s_info[jl * 8 + j] = (uint8_t)(T | flags);
+            }
+            __syncwarp();
+            // P3b: the junction's candidates in settle order of the neighbours, then the sequential rule
+            float cc[CS3_MAX_LINKS];
+            uint32_t cu[CS3_MAX_LINKS], cd[CS3_MAX_LINKS], crk[CS3_MAX_LINKS], cj[CS3_MAX_LINKS];
+            int ncand = 0;
+            uint32_t pmask_c = 0;
+            if (valid) {
+                const float av = __uint_as_float(avb);
                 unsigned long long info8 = 0ull;
                 for (uint32_t j = 0; j < deg; ++j) {
-                    const CsView V = cs3_view(g, S, v, off, j);
-                    const uint32_t k = V.k;
-                    const uint2 dF = cs_ld(&A.ds[V.far]);
-                    const uint32_t fid = V.far == J ? S.id : V.far;
-                    // walk from F toward v: CS3_W(t) = distance of m_t via F (t = k .. 1), inf where not reached
-                    for (uint32_t t = 1; t <= k; ++t) CS3_W(t) = __uint_as_float(INF);
-                    if (dF.x != INF) {
-                        float b = __uint_as_float(dF.x);
-                        for (uint32_t t = 0; t < k; ++t) {
-                            const float nb2 = __fadd_rn(b, __ldg(&g.csec[V.sF + t]));
-                            if (nb2 > p.max_seconds) break;
-                            if (nb2 == b) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
-                            b = nb2;
-                            CS3_W(k - t) = b;
-                        }
+                    info8 |= (unsigned long long)s_info[lane * 8 + j] << (8 * j);
+                    const uint32_t ud = s_cd[lane * 8 + j];
+                    if (ud == INF) continue;
+                    const uint32_t uidp = s_cu[lane * 8 + j];
+                    const uint32_t uid = uidp & 0x0fffffffu, paf = uidp >> 28;
+                    int q = ncand++;
+                    while (q > 0) {
+                        const bool gt = cd[q - 1] != ud ? cd[q - 1] > ud
+                                        : cu[q - 1] != uid ? cs3_key(g, S, cu[q - 1]) > cs3_key(g, S, uid)
+                                                           : (cj[q - 1] >> 8) > paf;
+                        if (!gt) break;
+                        cc[q] = cc[q - 1];
+                        cu[q] = cu[q - 1];
+                        cd[q] = cd[q - 1];
+                        crk[q] = crk[q - 1];
+                        cj[q] = cj[q - 1];
+                        --q;
                     }
-                    // the neighbour on this link (m_1, or F itself) as a candidate predecessor of v
-                    const uint32_t ud = k == 0 ? dF.x : __float_as_uint(CS3_W(1));
-                    const uint32_t uid = k == 0 ? fid : V.id1;
-                    if (ud != INF && r != 0) {
-                        const bool before = k == 0 ? (dF.y < r) : cs3_before(g, S, ud, uid, avb, vid);
-                        if (before) {
-                            const float c = __fadd_rn(__uint_as_float(ud), __ldg(&g.csec[V.sF + k]));
-                            if (p.phase2 || !(c > p.max_seconds)) {
-                                // insertion by settle order of the neighbour, then its in-list position
-                                int q = ncand++;
-                                while (q > 0) {
-                                    const bool gt = cd[q - 1] != ud ? cd[q - 1] > ud
-                                                    : cu[q - 1] != uid
-                                                        ? cs3_key(g, S, cu[q - 1]) > cs3_key(g, S, uid)
-                                                        : (cj[q - 1] >> 8) > V.paf;
-                                    if (!gt) break;
-                                    cc[q] = cc[q - 1];
-                                    cu[q] = cu[q - 1];
-                                    cd[q] = cd[q - 1];
-                                    crk[q] = crk[q - 1];
-                                    cj[q] = cj[q - 1];
-                                    --q;
-                                }
-                                cc[q] = c;
-                                cu[q] = uid;
-                                cd[q] = ud;
-                                crk[q] = dF.y;  // sigma of the neighbour = sigma of F (one-predecessor run)
-                                cj[q] = j | (V.paf << 8);
-                            }
-                        }
-                    }
-                    // own side of the chain: m_1 .. m_T are reached from v first
-                    const bool wins = dF.x != INF && (dF.y > r || (dF.y == r && j < V.paf));  // ties and shared pieces
-                    uint32_t T = 0;
-                    float a = av, a_prev = av;  // a = distance of m_T (v when T == 0), a_prev that of m_{T-1}
-                    for (uint32_t t = 1; t <= k; ++t) {
-                        const float na = __fadd_rn(a, __ldg(&g.csec[V.sv + t - 1]));
-                        if (na > p.max_seconds) break;
-                        if (na == a) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
-                        const float bt = CS3_W(t);
-                        if (!(na < bt || (na == bt && (dF.x == INF || wins)))) break;
-                        a_prev = a;
-                        a = na;
-                        T = t;
-                        if (p.closeness) {
-                            const int th = cs3_first_threshold<DT>(p, __fmul_rn(na, p.speed));
-                            atomicAdd(&histN[th], 1u);
-                            atomicAdd(&histE[th], 1u);  // piece (m_{t-1}, m_t): the larger cost is m_t's
-                        }
-                    }
-                    n_interior += T;
-                    uint32_t flags = 0;
-                    // meeting pair X = m_T (v when T == 0), Y = m_{T+1} (F when T == k)
-                    const uint32_t yd = T == k ? dF.x : __float_as_uint(CS3_W(T + 1));
-                    if (yd != INF) {
-                        const float ydf = __uint_as_float(yd);
-                        if (p.closeness && V.cnt && (dF.y > r || (dF.y == r && j < V.paf))) {
-                            const float ec = __fmul_rn(fmaxf(a, ydf), p.speed);
-                            atomicAdd(&histE[cs3_first_threshold<DT>(p, ec)], V.cnt);
-                        }
-                        const uint32_t xid = T == 0 ? vid : V.id1 + V.step * (int)(T - 1);
-                        const uint32_t yid = T == k ? fid : V.id1 + V.step * (int)T;
-                        const bool x_later = cs3_before(g, S, yd, yid, __float_as_uint(a), xid);
-                        if (x_later && T >= 1) {
-                            // X has its own-side predecessor m_{T-1} and, perhaps, Y
-                            const float c_oth = __fadd_rn(ydf, __ldg(&g.csec[V.sF + (k - T)]));
-                            const uint32_t pid = T == 1 ? vid : V.id1 + V.step * (int)(T - 2);
-                            const bool own_first = cs3_before(g, S, __float_as_uint(a_prev), pid, yd, yid);
-                            if (cs3_other_kept(a, c_oth, own_first, p.phase2 != 0, one_plus_tol, p.max_seconds)) flags |= 0x10u;
-                        } else if (!x_later && T < k) {
-                            // Y (an interior on F's side) has its own predecessor m_{T+2} / F and, perhaps, X
-                            const float c_oth = __fadd_rn(a, __ldg(&g.csec[V.sv + T]));
-                            const uint32_t qd = T + 1 == k ? dF.x : __float_as_uint(CS3_W(T + 2));
-                            const uint32_t qid = T + 1 == k ? fid : V.id1 + V.step * (int)(T + 1);
-                            const bool own_first = cs3_before(g, S, qd, qid, __float_as_uint(a), xid);
-                            if (cs3_other_kept(ydf, c_oth, own_first, p.phase2 != 0, one_plus_tol, p.max_seconds)) flags |= 0x20u;
-                        }
-                    }
-                    info8 |= (unsigned long long)(T | flags) << (8 * j);
+                    cc[q] = s_cc[lane * 8 + j];
+                    cu[q] = uid;
+                    cd[q] = ud;
+                    crk[q] = s_cr[lane * 8 + j];
+                    cj[q] = j | (paf << 8);
                 }
                 cs_st(reinterpret_cast<unsigned long long*>(linfo + (size_t)r * 8), info8);
                 if (ncand == 1 && !p.phase2) {
@@ -592,14 +683,18 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                     }
                 }
                 uint32_t amask = 0;
-                for (uint32_t mm = pmask_c; mm; mm &= mm - 1) amask |= 1u << (cj[__ffs(mm) - 1] & 0xffu);
+                for (uint32_t mm = pmask_c; mm; mm &= mm - 1) {
+                    const int q = __ffs(mm) - 1;
+                    amask |= 1u << (cj[q] & 0xffu);
+                    atomicMin(&minsucc[crk[q]], r);  // P5 forms chunks whose junctions do not depend on each other
+                }
                 cs_st(&A.predmask[r], amask);
                 if (r == 0) cs_st(&A.sigma[r], 1.0);
             }
             bool pending = valid && r != 0;
             for (;;) {
                 if (pending) {
-                    double s = 0.0;
+                    double sg_sum = 0.0;
                     bool ok = true;
                     for (uint32_t mm = pmask_c; mm; mm &= mm - 1) {
                         const double sg = cs_ld(&A.sigma[crk[__ffs(mm) - 1]]);
@@ -607,14 +702,14 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                             ok = false;
                             break;
                         }
-                        s += sg;
+                        sg_sum += sg;
                     }
                     if (ok) {
-                        if (s == 0.0) {
+                        if (sg_sum == 0.0) {
                             atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);  // reached without an earlier-settled predecessor
-                            s = 1.0;
+                            sg_sum = 1.0;
                         }
-                        cs_st(&A.sigma[r], s);
+                        cs_st(&A.sigma[r], sg_sum);
                         pending = false;
                     }
                 }
@@ -624,6 +719,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
         }
         __syncwarp();
         tc[3] = clock64();
+        CS3_BAR();
 
         // ------------------------------------------------------------------ P4: closeness scatter to targets
         unsigned long long n_ri = 0, n_ci = 0;
@@ -691,172 +787,246 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
         }
         __syncwarp();
         tc[4] = clock64();
+        CS3_BAR();
 
         // ------------------------------------------------------------------ P5: dependencies, reverse settle order
+        // Chunks are formed so that no junction of a chunk depends on another one of the same chunk (minsucc): nothing
+        // waits.  Per chunk: one lane per LINK stages its own-side interiors; the seeds (f64 exp) are formed with one lane
+        // per node; the lane of the link runs the sequential f64 recurrence of its chain (centrality.rs:823-873) over the
+        // staged seeds and leaves the credits in shared memory; they are scattered with one lane per node (consecutive
+        // ids, metric-major rows); the link's outflow is added to its junction in link order.
         if (p.betweenness) {
             const double wt_d = (double)wt;
-            for (int b0 = (int)((R - 1) & ~31u); b0 >= 0; b0 -= 32) {
-                const uint32_t r = (uint32_t)b0 + lane;
-                const bool valid = r < R;
+            int hi = (int)R - 1;
+            while (hi >= 0) {
+                const int rr = hi - (int)lane;
+                const uint32_t ms = rr >= 0 ? cs_ld(&minsucc[rr]) : 0u;
+                const uint32_t badm = __ballot_sync(CS_FULL, rr < 0 || ms <= (uint32_t)hi);
+                const uint32_t cnt = badm ? (uint32_t)__ffs(badm) - 1u : 32u;  // >= 1: minsucc[hi] > hi
+                const bool valid = lane < cnt;
+                const uint32_t r = (uint32_t)(hi - (int)lane);
                 uint32_t w = 0, off = 0, deg = 0;
-                uint32_t frk[CS3_MAX_LINKS];  // rank of F where F depends on this junction through link j
-                uint32_t need = 0, same_chunk = 0;
-                double sigma_w = 1.0;
                 float aw = 0.f;
-                unsigned long long info8 = 0ull;
+                double sigma_w = 1.0;
                 if (valid) {
                     w = cs_ld(&A.s_node[r]);
                     aw = cs_ld(&A.s_agg[r]);
                     sigma_w = cs_ld(&A.sigma[r]);
-                    info8 = cs_ld(reinterpret_cast<const unsigned long long*>(linfo + (size_t)r * 8));
                     deg = 2;
                     if (w != J) {
                         const uint2 ji = __ldg(&g.jinfo[w]);
                         off = ji.x;
                         deg = ji.y & 0xffu;
                     }
-                    for (uint32_t j = 0; j < deg; ++j) {
-                        const CsView V = cs3_view(g, S, w, off, j);
-                        const uint32_t T = (uint32_t)(info8 >> (8 * j)) & 15u;
-                        frk[j] = CS_NOSLOT;
-                        if (T != V.k) continue;
-                        const uint2 dF = cs_ld(&A.ds[V.far]);
-                        if (dF.x == INF || dF.y <= r) continue;
-                        if ((cs_ld(&A.predmask[dF.y]) >> V.paf) & 1u) {
-                            frk[j] = dF.y;
-                            need |= 1u << j;
-                            if (dF.y < (uint32_t)b0 + 32u) same_chunk |= 1u << j;
-                        }
-                    }
                 }
-                bool pending = valid;
-                for (;;) {
-                    if (pending) {
-                        bool ok = true;
-                        for (uint32_t mm = same_chunk; mm; mm &= mm - 1) ok = ok && (cs_ld(&bdone[frk[__ffs(mm) - 1]]) != 0);
-                        if (ok) {
-                            double acc[DT], accb[DT];
+                uint32_t inc = deg;
 #pragma unroll
-                            for (int i = 0; i < DT; ++i) acc[i] = accb[i] = 0.0;
-                            for (uint32_t j = 0; j < deg; ++j) {
-                                const uint32_t ib = (uint32_t)(info8 >> (8 * j)) & 0xffu;
-                                const uint32_t T = ib & 15u;
-                                const bool tie2 = (ib & 0x10u) != 0, yhas = (ib & 0x20u) != 0;
-                                const bool needF = (need >> j) & 1u;
-                                if (T == 0 && !needF && !yhas) continue;
-                                const CsView V = cs3_view(g, S, w, off, j);
-                                const uint32_t k = V.k;
-                                double dl[DT], dlb[DT];  // dependency flowing toward this junction along the link
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(CS_FULL, inc, o);
+                    if ((int)lane >= o) inc += t;
+                }
+                const uint32_t totalL = __shfl_sync(CS_FULL, inc, 31);
+                __syncwarp();
+                if (valid) {
+                    const unsigned long long info8 = cs_ld(reinterpret_cast<const unsigned long long*>(linfo + (size_t)r * 8));
+                    *reinterpret_cast<unsigned long long*>(s_info + lane * 8) = info8;
+                    for (uint32_t j = 0; j < deg; ++j) s_llist[inc - deg + j] = (uint16_t)(lane | (j << 5));
+                }
 #pragma unroll
-                                for (int i = 0; i < DT; ++i) dl[i] = dlb[i] = 0.0;
-                                double sigma_F = 0.0;
-                                if (needF || yhas || tie2) sigma_F = cs_ld(&A.sigma[cs_ld(&A.ds[V.far].y)]);
-                                if (needF) {
-                                    // the whole chain is on this side and F continues the path (centrality.rs:861-866)
-                                    const double f = (sigma_F == sigma_w) ? 1.0 : sigma_w / sigma_F;
-                                    const double* dx = A.dep + (size_t)frk[j] * D2;
+                for (int i = 0; i < 2 * DT; ++i) s_acc[i * 32 + lane] = 0.0;
+                __syncwarp();
+                for (uint32_t base = 0; base < totalL; base += 32) {
+                    const uint32_t e = base + lane;
+                    const bool act = e < totalL;
+                    const uint32_t code = act ? s_llist[e] : 0u;
+                    const uint32_t jl = code & 31u, j = code >> 5;
+                    const uint32_t lw = __shfl_sync(CS_FULL, w, jl), loff = __shfl_sync(CS_FULL, off, jl);
+                    const float law = __shfl_sync(CS_FULL, aw, jl);
+                    const double lsig = __shfl_sync(CS_FULL, sigma_w, jl);
+                    const uint32_t lr = (uint32_t)(hi - (int)jl);
+                    uint32_t T = 0;
+                    bool tie2 = false, work = false;
+                    double dl[DT], dlb[DT];  // dependency flowing toward the junction along this link
 #pragma unroll
-                                    for (int i = 0; i < DT; ++i) {
-                                        if (i < D) {
-                                            dl[i] = f * cs_ld(&dx[i]);
-                                            dlb[i] = f * cs_ld(&dx[D + i]);
-                                        }
-                                    }
-                                } else if (yhas) {
-                                    // Y = m_{T+1} was reached from F but keeps m_T (or this junction) as a second
-                                    // predecessor: it is the last-settled node of the chain, so its dependency is its seed
-                                    float b = __uint_as_float(cs_ld(&A.ds[V.far].x));
-                                    for (uint32_t t = 0; t < k - T; ++t) b = __fadd_rn(b, __ldg(&g.csec[V.sF + t]));
-                                    const float cost_y = __fmul_rn(b, p.speed);
-                                    const uint32_t yid = V.id1 + V.step * (int)T;
-                                    const double pc = __ldg(&p.eligible[yid]) ? 0.5 : 1.0;
-                                    const double f = sigma_w / (sigma_F + sigma_w);
-#pragma unroll
-                                    for (int i = 0; i < DT; ++i) {
-                                        if (i < D && cost_y <= p.dist_f[i]) {
-                                            dl[i] = f * pc;
-                                            dlb[i] = f * (pc * exp(-p.beta_d[i] * (double)cost_y));
-                                        }
-                                    }
-                                }
-                                if (T) {
-                                    float a = aw;
-                                    for (uint32_t t = 1; t <= T; ++t) {
-                                        a = __fadd_rn(a, __ldg(&g.csec[V.sv + t - 1]));
-                                        CS3_W(t) = a;
-                                    }
-                                    for (uint32_t t = T; t >= 1; --t) {
-                                        const float cost_t = __fmul_rn(CS3_W(t), p.speed);
-                                        const uint32_t id = V.id1 + V.step * (int)(t - 1);
-                                        const double pc = __ldg(&p.eligible[id]) ? 0.5 : 1.0;
-                                        // m_T with two predecessors has sigma_w + sigma_F paths (the source never sits here)
-                                        const double f = (t == T && tie2) ? sigma_w / (sigma_w + sigma_F) : 1.0;
-                                        double* row = p.acc_b + id;
-#pragma unroll
-                                        for (int i = 0; i < DT; ++i) {
-                                            if (i < D) {
-                                                double seed = 0.0, seedb = 0.0;
-                                                if (cost_t <= p.dist_f[i]) {
-                                                    seed = pc;
-                                                    seedb = pc * exp(-p.beta_d[i] * (double)cost_t);
-                                                }
-                                                const double dpn = seed + dl[i], dpb = seedb + dlb[i];
-                                                const double credit = dpn - seed, creditb = dpb - seedb;
-                                                if (credit > 0.0 || creditb > 0.0) {
-                                                    ++n_ci;
-                                                    if (credit > 0.0) cs_red_add(row + (size_t)(2 * i) * g.n, credit * wt_d);
-                                                    if (creditb > 0.0) cs_red_add(row + (size_t)(2 * i + 1) * g.n, creditb * wt_d);
-                                                }
-                                                dl[i] = f * dpn;
-                                                dlb[i] = f * dpb;
-                                            }
-                                        }
-                                    }
-                                }
-#pragma unroll
-                                for (int i = 0; i < DT; ++i) {
-                                    acc[i] += dl[i];
-                                    accb[i] += dlb[i];
-                                }
-                            }
-                            const bool is_src = r == 0;
-                            const uint32_t wid = w == J ? S.id : w;
-                            const float cost_w = __fmul_rn(aw, p.speed);
-                            const double pc = is_src ? 0.0 : (__ldg(&p.eligible[wid]) ? 0.5 : 1.0);
-                            double* dr = A.dep + (size_t)r * D2;
-                            double* row = p.acc_b + wid;
+                    for (int i = 0; i < DT; ++i) dl[i] = dlb[i] = 0.0;
+                    CsView V;
+                    V.sv = V.id1 = 0;
+                    V.step = 1;
+                    double fT = 1.0;
+                    if (act) {
+                        const uint32_t ib = s_info[jl * 8 + j];
+                        T = ib & 15u;
+                        tie2 = (ib & 0x10u) != 0;
+                        const bool yhas = (ib & 0x20u) != 0;
+                        V = cs3_view(g, S, lw, loff, j);
+                        const uint32_t k = V.k;
+                        bool needF = false;
+                        uint2 dF = make_uint2(INF, CS_NOSLOT);
+                        if (T == k || yhas || tie2) dF = cs_ld(&A.ds[V.far]);
+                        if (T == k && dF.x != INF && dF.y > lr) needF = (cs_ld(&A.predmask[dF.y]) >> V.paf) & 1u;
+                        work = T > 0 || needF || yhas;
+                        double sigma_F = 0.0;
+                        if (needF || yhas || tie2) sigma_F = cs_ld(&A.sigma[dF.y]);
+                        if (needF) {
+                            // the whole chain is on this side and F continues the path (centrality.rs:861-866)
+                            const double f = (sigma_F == lsig) ? 1.0 : lsig / sigma_F;
+                            const double* dx = A.dep + (size_t)dF.y * D2;
 #pragma unroll
                             for (int i = 0; i < DT; ++i) {
                                 if (i < D) {
-                                    double seed = 0.0, seedb = 0.0;
-                                    if (!is_src && cost_w <= p.dist_f[i]) {
-                                        seed = pc;
-                                        seedb = pc * exp(-p.beta_d[i] * (double)cost_w);
+                                    dl[i] = f * cs_ld(&dx[i]);
+                                    dlb[i] = f * cs_ld(&dx[D + i]);
+                                }
+                            }
+                        } else if (yhas) {
+                            // Y = m_{T+1} was reached from F but keeps m_T (or this junction) as a second predecessor:
+                            // it is the last-settled node of the chain, so its dependency is its seed
+                            float b = __uint_as_float(dF.x);
+                            for (uint32_t t = 0; t < k - T; ++t) b = __fadd_rn(b, __ldg(&g.csec[V.sF + t]));
+                            const float cost_y = __fmul_rn(b, p.speed);
+                            const uint32_t yid = V.id1 + V.step * (int)T;
+                            const double pc = __ldg(&p.eligible[yid]) ? 0.5 : 1.0;
+                            const double f = lsig / (sigma_F + lsig);
+#pragma unroll
+                            for (int i = 0; i < DT; ++i) {
+                                if (i < D && cost_y <= p.dist_f[i]) {
+                                    dl[i] = f * pc;
+                                    dlb[i] = f * (pc * cs3_exp(-p.beta_d[i] * (double)cost_y));
+                                }
+                            }
+                        }
+                        // m_T with two predecessors carries sigma_w + sigma_F paths
+                        if (tie2) fT = lsig / (lsig + sigma_F);
+                    }
+                    // sub-iterations: as many links as fit the node staging area
+                    uint32_t remaining = __ballot_sync(CS_FULL, act && work);
+                    while (remaining) {
+                        const bool mine = (remaining >> lane) & 1u;
+                        uint32_t tinc = mine ? T : 0u;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t t = __shfl_up_sync(CS_FULL, tinc, o);
+                            if ((int)lane >= o) tinc += t;
+                        }
+                        const bool go = mine && tinc <= NB;
+                        const uint32_t gom = __ballot_sync(CS_FULL, go);
+                        const uint32_t last = 31u - (uint32_t)__clz(gom);
+                        const uint32_t total = __shfl_sync(CS_FULL, tinc, last);
+                        const uint32_t offs = tinc - T;
+                        __syncwarp();
+                        if (go) {
+                            float a = law;
+                            for (uint32_t t = 1; t <= T; ++t) {
+                                a = __fadd_rn(a, __ldg(&g.csec[V.sv + t - 1]));
+                                s_ids[offs + t - 1] = V.id1 + V.step * (int)(t - 1);
+                                s_cst[offs + t - 1] = __fmul_rn(a, p.speed);
+                            }
+                        }
+                        __syncwarp();
+                        // seeds, one lane per node (centrality.rs:1802-1806)
+                        for (uint32_t e0 = 0; e0 < total; e0 += 32) {
+                            const uint32_t en = e0 + lane;
+                            if (en < total) {
+                                const float cost = s_cst[en];
+                                const double pc = __ldg(&p.eligible[s_ids[en]]) ? 0.5 : 1.0;
+                                s_pcs[en] = (float)pc;
+#pragma unroll
+                                for (int i = 0; i < DT; ++i)
+                                    if (i < D) s_crd[(2 * i + 1) * NB + en] = cost <= p.dist_f[i] ? pc * cs3_exp(-p.beta_d[i] * (double)cost) : 0.0;
+                            }
+                        }
+                        __syncwarp();
+                        if (go) {
+                            for (uint32_t t = T; t >= 1; --t) {
+                                const uint32_t en = offs + t - 1;
+                                const float cost = s_cst[en];
+                                const double pc = (double)s_pcs[en];
+                                const double f = t == T ? fT : 1.0;
+#pragma unroll
+                                for (int i = 0; i < DT; ++i) {
+                                    if (i < D) {
+                                        const double seed = cost <= p.dist_f[i] ? pc : 0.0;
+                                        const double seedb = s_crd[(2 * i + 1) * NB + en];
+                                        const double dpn = seed + dl[i], dpb = seedb + dlb[i];
+                                        s_crd[(2 * i) * NB + en] = dpn - seed;
+                                        s_crd[(2 * i + 1) * NB + en] = dpb - seedb;
+                                        dl[i] = f * dpn;
+                                        dlb[i] = f * dpb;
                                     }
-                                    const double dpn = seed + acc[i], dpb = seedb + accb[i];
-                                    cs_st(&dr[i], dpn);
-                                    cs_st(&dr[D + i], dpb);
-                                    if (!is_src) {
-                                        const double credit = dpn - seed, creditb = dpb - seedb;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        // credits, one lane per node
+                        for (uint32_t e0 = 0; e0 < total; e0 += 32) {
+                            const uint32_t en = e0 + lane;
+                            if (en < total) {
+                                double* col = p.acc_b + s_ids[en];
+#pragma unroll
+                                for (int i = 0; i < DT; ++i) {
+                                    if (i < D) {
+                                        const double credit = s_crd[(2 * i) * NB + en], creditb = s_crd[(2 * i + 1) * NB + en];
                                         if (credit > 0.0 || creditb > 0.0) {
                                             ++n_ci;
-                                            if (credit > 0.0) cs_red_add(row + (size_t)(2 * i) * g.n, credit * wt_d);
-                                            if (creditb > 0.0) cs_red_add(row + (size_t)(2 * i + 1) * g.n, creditb * wt_d);
+                                            if (credit > 0.0) cs_red_add(col + (size_t)(2 * i) * g.n, credit * wt_d);
+                                            if (creditb > 0.0) cs_red_add(col + (size_t)(2 * i + 1) * g.n, creditb * wt_d);
                                         }
                                     }
                                 }
                             }
-                            __threadfence_block();
-                            cs_st(&bdone[r], (uint8_t)1);
-                            pending = false;
+                        }
+                        // outflow into the junction, link by link (ascending j: the reference's accumulation order)
+                        for (uint32_t sl = 0; sl < CS3_MAX_LINKS; ++sl) {
+                            if (go && j == sl) {
+#pragma unroll
+                                for (int i = 0; i < DT; ++i) {
+                                    if (i < D) {
+                                        s_acc[i * 32 + jl] += dl[i];
+                                        s_acc[(DT + i) * 32 + jl] += dlb[i];
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        remaining &= ~gom;
+                    }
+                }
+                __syncwarp();
+                if (valid) {
+                    const bool is_src = r == 0;
+                    const uint32_t wid = w == J ? S.id : w;
+                    const float cost_w = __fmul_rn(aw, p.speed);
+                    const double pc = is_src ? 0.0 : (__ldg(&p.eligible[wid]) ? 0.5 : 1.0);
+                    double* dr = A.dep + (size_t)r * D2;
+                    double* col = p.acc_b + wid;
+#pragma unroll
+                    for (int i = 0; i < DT; ++i) {
+                        if (i < D) {
+                            double seed = 0.0, seedb = 0.0;
+                            if (!is_src && cost_w <= p.dist_f[i]) {
+                                seed = pc;
+                                seedb = pc * cs3_exp(-p.beta_d[i] * (double)cost_w);
+                            }
+                            const double dpn = seed + s_acc[i * 32 + lane], dpb = seedb + s_acc[(DT + i) * 32 + lane];
+                            cs_st(&dr[i], dpn);
+                            cs_st(&dr[D + i], dpb);
+                            if (!is_src) {
+                                const double credit = dpn - seed, creditb = dpb - seedb;
+                                if (credit > 0.0 || creditb > 0.0) {
+                                    ++n_ci;
+                                    if (credit > 0.0) cs_red_add(col + (size_t)(2 * i) * g.n, credit * wt_d);
+                                    if (creditb > 0.0) cs_red_add(col + (size_t)(2 * i + 1) * g.n, creditb * wt_d);
+                                }
+                            }
                         }
                     }
-                    __syncwarp();
-                    if (!__any_sync(CS_FULL, pending)) break;
                 }
+                __syncwarp();
+                hi -= (int)cnt;
             }
         }
         tc[5] = clock64();
+        CS3_BAR();
 
         // ------------------------------------------------------------------ P6: reset the dense map
         cs_p6_reset(A, R);
@@ -867,7 +1037,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
         n_ri = cs_warp_sum(n_ri);
         n_ci = cs_warp_sum(n_ci);
         n_interior = cs_warp_sum(n_interior);
-        if (lane == 0) {
+        if (lane == 0 && run) {
             atomicAdd(&p.counters[CS_C_SOURCES], 1ull);
             atomicAdd(&p.counters[CS_C_SETTLED], (unsigned long long)R + n_interior);
             atomicAdd(&p.counters[CS_C_EDGE_ITERS], edge_iters + 2ull * n_interior);
@@ -880,6 +1050,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
         }
     }
 #undef CS3_W
+#undef CS3_BAR
 }
 
 // Epilogue for the metric-major accumulators of the chain-contracted kernel: new-id columns -> [7][D][node_bound] in
@@ -902,4 +1073,10 @@ __global__ void cs_k_epilogue_shortest3(const double* __restrict__ acc_c, const 
             if (betweenness || !add) *o = add ? *o + val : val;
         }
     }
+}
+
+template <int DT>
+static constexpr uint32_t cs3_smem_bytes() {
+    constexpr uint32_t NB = DT <= 3 ? 128u : DT == 4 ? 96u : 24u;
+    return CS3_WARPS * (CS_NBINS * 4 + 2 * DT * NB * 8 + 2 * DT * 32 * 8 + 256 * 2 + 256);
 }
