@@ -246,6 +246,7 @@ static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, c
     for (uint32_t c = 0; c < NC; ++c) {
         const Chain& ch = chains[c];
         const uint32_t k = ch.k;
+        while (cnum.size() & 3u) cnum.push_back(0.f);  // blocks are fetched with 16-byte loads
         soff[c] = (uint32_t)cnum.size();
         auto node = [&](uint32_t t) { return t == 0 ? ch.A : t == k + 1 ? ch.B : ch.nodes[t - 1]; };
         std::vector<float> fwd(k + 1), bwd(k + 1);
@@ -263,10 +264,12 @@ static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, c
         for (uint32_t t = 0; t <= k; ++t) cnum.push_back(bwd[k - t]);
     }
     for (uint32_t d = 0; d < directs.size(); ++d) {
+        while (cnum.size() & 3u) cnum.push_back(0.f);
         soff[NC + d] = (uint32_t)cnum.size();
         cnum.push_back(in_num[directs[d].slotA]);  // B -> A: A's outward step
         cnum.push_back(in_num[directs[d].slotB]);  // A -> B: B's outward step
     }
+    while (cnum.size() & 3u) cnum.push_back(0.f);
     // ---- link records by new junction id
     std::vector<uint32_t> jn_off(J + 1, 0);
     for (uint32_t q = 0; q < J; ++q) jn_off[q + 1] = jn_off[q] + nlinks[jorder[q]];

@@ -58,7 +58,8 @@ struct CsShortest3Params {
 };
 
 struct CsView {
-    uint32_t far, sv, sF, k, id1, paf, cnt;
+    uint32_t far, sv, sF, k, id1, paf, cnt;  // sv / sF: offsets of the outward steps inside the chain's block
+    uint32_t blk, nv;                        // the block: float offset into csec, number of floats
     int step;
 };
 
@@ -72,17 +73,19 @@ __device__ __forceinline__ CsView cs3_view(const CsV3Graph& g, const CsSrc3& S, 
     if (v == g.J) {
         // the source sits inside a chain at position p (1-based): two links, toward A (0) and toward B (1)
         V.cnt = 1;
+        V.blk = S.soff;
+        V.nv = 2 * (S.k + 1);
         if (j == 0) {
-            V.sv = S.soff + (S.k + 1) + (S.k - S.p + 1);
-            V.sF = S.soff;
+            V.sv = (S.k + 1) + (S.k - S.p + 1);
+            V.sF = 0;
             V.k = S.p - 1;
             V.id1 = g.J + S.ibase + S.p - 2;
             V.step = -1;
             V.far = S.A;
             V.paf = S.posA;
         } else {
-            V.sv = S.soff + S.p;
-            V.sF = S.soff + (S.k + 1);
+            V.sv = S.p;
+            V.sF = S.k + 1;
             V.k = S.k - S.p;
             V.id1 = g.J + S.ibase + S.p;
             V.step = 1;
@@ -97,14 +100,16 @@ __device__ __forceinline__ CsView cs3_view(const CsV3Graph& g, const CsSrc3& S, 
     V.k = k;
     V.paf = (L.w >> 5) & 15u;
     V.cnt = (L.w >> 9) & 3u;
+    V.blk = L.y;
+    V.nv = 2 * (k + 1);
     if (dir == 0) {
-        V.sv = L.y;
-        V.sF = L.y + k + 1;
+        V.sv = 0;
+        V.sF = k + 1;
         V.id1 = g.J + L.z;
         V.step = 1;
     } else {
-        V.sv = L.y + k + 1;
-        V.sF = L.y;
+        V.sv = k + 1;
+        V.sF = 0;
         V.id1 = g.J + L.z + k - 1;
         V.step = -1;
     }
@@ -113,15 +118,26 @@ __device__ __forceinline__ CsView cs3_view(const CsV3Graph& g, const CsSrc3& S, 
         V.far = g.J;
         if (dir == 0) {
             V.k = S.p - 1;
-            V.sF = L.y + (k + 1) + (k - S.p + 1);
+            V.sF = (k + 1) + (k - S.p + 1);
             V.paf = 0;
         } else {
             V.k = k - S.p;
-            V.sF = L.y + S.p;
+            V.sF = S.p;
             V.paf = 1;
         }
     }
     return V;
+}
+
+// The seconds of a chain (both directions, <= 2 * (CS3_KMAX + 1) floats) are copied with independent asynchronous 4-byte
+// copies (LDGSTS, no registers) into the lane's column of a shared-memory scratch; the sequential f32 walks then run at
+// shared-memory latency instead of one dependent L2 round trip per piece.
+__device__ __forceinline__ void cs3_load_block(const CsV3Graph& g, const CsView& V, float* cb, uint32_t first, uint32_t count) {
+    const float* src = g.csec + V.blk + first;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(cb + first * 32);
+    for (uint32_t i = 0; i < count; ++i)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + i * 128u), "l"(src + i) : "memory");
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 // settle-order tie key of a node (new id): the source first, then ascending original index
@@ -200,10 +216,11 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
     // per-warp shared memory: region A (4 KB): P2 bins | P3 candidates | P4 staged (node, cost) list | P5 node ids / costs;
     // region B (6 KB): P3 walk values | P5 per-node seeds -> credits; region C: P3 / P5 link list, link bytes, P5 outflow
     constexpr uint32_t NB = DT <= 3 ? 128u : DT == 4 ? 96u : 24u;  // staged nodes per P5 sub-iteration
-    constexpr uint32_t BYTES_A = CS_NBINS * 4, BYTES_B = 2 * DT * NB * 8;
+    constexpr uint32_t WALK_BYTES = (CS3_KMAX + 2 + 28) * 32 * 4;
+    constexpr uint32_t BYTES_A = CS_NBINS * 4, BYTES_B = 2 * DT * NB * 8 > WALK_BYTES ? 2 * DT * NB * 8 : WALK_BYTES;
     constexpr uint32_t BYTES_C = 2 * DT * 32 * 8 + 256 * 2 + 256;
     constexpr uint32_t BYTES_W = BYTES_A + BYTES_B + BYTES_C;
-    static_assert(BYTES_B >= (CS3_KMAX + 2) * 32 * 4, "walk values must fit region B");
+    static_assert(BYTES_B >= (CS3_KMAX + 2 + 28) * 32 * 4, "walk values and the chain block must fit region B");
     static_assert(3 * NB * 4 <= BYTES_A && NB >= CS3_KMAX, "P5 node staging must fit region A");
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ uint32_t s_hist_all[CS3_WARPS][2][CS_MAX_THRESHOLDS + 1];
@@ -225,6 +242,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
     float* s_cst = reinterpret_cast<float*>(bins + NB);
     float* s_pcs = reinterpret_cast<float*>(bins + 2 * NB);
     float* walk = reinterpret_cast<float*>(s_warp + BYTES_A);
+    float* cblk = walk + (CS3_KMAX + 2) * 32 + lane;  // the lane's column of the chain-block scratch (28 rows)
     double* s_crd = reinterpret_cast<double*>(s_warp + BYTES_A);
     double* s_acc = reinterpret_cast<double*>(s_warp + BYTES_A + BYTES_B);
     uint16_t* s_llist = reinterpret_cast<uint16_t*>(s_warp + BYTES_A + BYTES_B + 2 * DT * 32 * 8);
@@ -233,6 +251,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
     uint32_t* histE = s_hist_all[wic][1];
     float* rankf = s_rank_all[wic];
 #define CS3_W(t) walk[(t) * 32 + lane]
+#define CS3_CB(i) cblk[(i) * 32]
     const CsWarpArena A = cs_arena(p.arena, p.lay, worker);
     uint8_t* linfo = A.bdone;          // [rcap][8] link bytes: T | tie2 << 4 | yhas << 5
     uint32_t* minsucc = A.node_list;   // [rcap] after P2: smallest rank that has this junction as a predecessor
@@ -337,10 +356,11 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                             float cand = 0.f;
                             if (j < deg && j != skip) {
                                 const CsView V = cs3_view(g, S, v, off, j);
+                                cs3_load_block(g, V, cblk, V.sv, V.k + 1);
                                 float a = __uint_as_float(abits);
                                 bool ok = true;
                                 for (uint32_t t = 0; t <= V.k; ++t) {
-                                    a = __fadd_rn(a, __ldg(&g.csec[V.sv + t]));
+                                    a = __fadd_rn(a, CS3_CB(V.sv + t));
                                     if (a > p.max_seconds) {
                                         ok = false;
                                         break;
@@ -538,6 +558,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 const uint32_t lr = b0 + jl;
                 const float av = __uint_as_float(lavb);
                 const CsView V = cs3_view(g, S, lv, loff, j);
+                cs3_load_block(g, V, cblk, 0, V.nv);
                 const uint32_t k = V.k;
                 const uint2 dF = cs_ld(&A.ds[V.far]);
                 const uint32_t fid = V.far == J ? S.id : V.far;
@@ -546,7 +567,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 if (dF.x != INF) {
                     float b = __uint_as_float(dF.x);
                     for (uint32_t t = 0; t < k; ++t) {
-                        const float nb2 = __fadd_rn(b, __ldg(&g.csec[V.sF + t]));
+                        const float nb2 = __fadd_rn(b, CS3_CB(V.sF + t));
                         if (nb2 > p.max_seconds) break;
                         if (nb2 == b) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
                         b = nb2;
@@ -561,7 +582,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 if (ud != INF && lr != 0) {
                     const bool before = k == 0 ? (dF.y < lr) : cs3_before(g, S, ud, uid, lavb, lvid);
                     if (before) {
-                        const float c = __fadd_rn(__uint_as_float(ud), __ldg(&g.csec[V.sF + k]));
+                        const float c = __fadd_rn(__uint_as_float(ud), CS3_CB(V.sF + k));
                         if (p.phase2 || !(c > p.max_seconds)) {
                             c_ud = ud;
                             c_c = c;
@@ -577,7 +598,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 uint32_t T = 0;
                 float a = av, a_prev = av;  // a = distance of m_T (v when T == 0), a_prev that of m_{T-1}
                 for (uint32_t t = 1; t <= k; ++t) {
-                    const float na = __fadd_rn(a, __ldg(&g.csec[V.sv + t - 1]));
+                    const float na = __fadd_rn(a, CS3_CB(V.sv + t - 1));
                     if (na > p.max_seconds) break;
                     if (na == a) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
                     const float bt = CS3_W(t);
@@ -606,13 +627,13 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                     const bool x_later = cs3_before(g, S, yd, yid, __float_as_uint(a), xid);
                     if (x_later && T >= 1) {
                         // X has its own-side predecessor m_{T-1} and, perhaps, Y
-                        const float c_oth = __fadd_rn(ydf, __ldg(&g.csec[V.sF + (k - T)]));
+                        const float c_oth = __fadd_rn(ydf, CS3_CB(V.sF + (k - T)));
                         const uint32_t pid = T == 1 ? lvid : V.id1 + V.step * (int)(T - 2);
                         const bool own_first = cs3_before(g, S, __float_as_uint(a_prev), pid, yd, yid);
                         if (cs3_other_kept(a, c_oth, own_first, p.phase2 != 0, one_plus_tol, p.max_seconds)) flags |= 0x10u;
                     } else if (!x_later && T < k) {
                         // Y (an interior on F's side) has its own predecessor m_{T+2} / F and, perhaps, X
-                        const float c_oth = __fadd_rn(a, __ldg(&g.csec[V.sv + T]));
+                        const float c_oth = __fadd_rn(a, CS3_CB(V.sv + T));
                         const uint32_t qd = T + 1 == k ? dF.x : __float_as_uint(CS3_W(T + 2));
                         const uint32_t qid = T + 1 == k ? fid : V.id1 + V.step * (int)(T + 1);
                         const bool own_first = cs3_before(g, S, qd, qid, __float_as_uint(a), xid);
@@ -772,10 +793,11 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                     __syncwarp();
                     if (T) {
                         const CsView V = cs3_view(g, S, v, off, j);
+                        cs3_load_block(g, V, cblk, V.sv, T);
                         uint32_t pos = inc - T;
                         float a = av;
                         for (uint32_t t = 1; t <= T; ++t, ++pos) {
-                            a = __fadd_rn(a, __ldg(&g.csec[V.sv + t - 1]));
+                            a = __fadd_rn(a, CS3_CB(V.sv + t - 1));
                             l_id[pos] = V.id1 + V.step * (int)(t - 1);
                             l_cost[pos] = __fmul_rn(a, p.speed);
                         }
@@ -881,8 +903,9 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                         } else if (yhas) {
                             // Y = m_{T+1} was reached from F but keeps m_T (or this junction) as a second predecessor:
                             // it is the last-settled node of the chain, so its dependency is its seed
+                            cs3_load_block(g, V, cblk, V.sF, k - T);
                             float b = __uint_as_float(dF.x);
-                            for (uint32_t t = 0; t < k - T; ++t) b = __fadd_rn(b, __ldg(&g.csec[V.sF + t]));
+                            for (uint32_t t = 0; t < k - T; ++t) b = __fadd_rn(b, CS3_CB(V.sF + t));
                             const float cost_y = __fmul_rn(b, p.speed);
                             const uint32_t yid = V.id1 + V.step * (int)T;
                             const double pc = __ldg(&p.eligible[yid]) ? 0.5 : 1.0;
@@ -914,10 +937,11 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                         const uint32_t total = __shfl_sync(CS_FULL, tinc, last);
                         const uint32_t offs = tinc - T;
                         __syncwarp();
-                        if (go) {
+                        if (go && T) {
+                            cs3_load_block(g, V, cblk, V.sv, T);
                             float a = law;
                             for (uint32_t t = 1; t <= T; ++t) {
-                                a = __fadd_rn(a, __ldg(&g.csec[V.sv + t - 1]));
+                                a = __fadd_rn(a, CS3_CB(V.sv + t - 1));
                                 s_ids[offs + t - 1] = V.id1 + V.step * (int)(t - 1);
                                 s_cst[offs + t - 1] = __fmul_rn(a, p.speed);
                             }
@@ -1050,6 +1074,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
         }
     }
 #undef CS3_W
+#undef CS3_CB
 #undef CS3_BAR
 }
 
@@ -1078,5 +1103,7 @@ __global__ void cs_k_epilogue_shortest3(const double* __restrict__ acc_c, const 
 template <int DT>
 static constexpr uint32_t cs3_smem_bytes() {
     constexpr uint32_t NB = DT <= 3 ? 128u : DT == 4 ? 96u : 24u;
-    return CS3_WARPS * (CS_NBINS * 4 + 2 * DT * NB * 8 + 2 * DT * 32 * 8 + 256 * 2 + 256);
+    constexpr uint32_t WALK_BYTES = (CS3_KMAX + 2 + 28) * 32 * 4;
+    constexpr uint32_t B = 2 * DT * NB * 8 > WALK_BYTES ? 2 * DT * NB * 8 : WALK_BYTES;
+    return CS3_WARPS * (CS_NBINS * 4 + B + 2 * DT * 32 * 8 + 256 * 2 + 256);
 }
