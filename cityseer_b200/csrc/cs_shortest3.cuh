@@ -173,7 +173,7 @@ __device__ __forceinline__ int cs3_first_threshold(const CsShortest3Params& p, f
     int ti = DT;
 #pragma unroll
     for (int i = DT - 1; i >= 0; --i)
-        if (i < p.D && cost <= p.dist_f[i]) ti = i;
+        if ((DT <= 4 || i < p.D) && cost <= p.dist_f[i]) ti = i;
     return ti;
 }
 
@@ -197,7 +197,7 @@ __device__ __forceinline__ void cs3_emit_closeness(const CsShortest3Params& p, c
             const double wt_t = (double)wt;
 #pragma unroll
             for (int i = 0; i < DT; ++i) {
-                if (i < p.D && cost <= p.dist_f[i]) {
+                if ((DT <= 4 || i < p.D) && cost <= p.dist_f[i]) {
                     ++n_ri;
                     double* q = base + (size_t)(5 * i) * n;
                     cs_red_add(q, wt_t);
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
     uint32_t* minsucc = A.node_list;   // [rcap] after P2: smallest rank that has this junction as a predecessor
     const CsV3Graph& g = p.g;
     const uint32_t J = g.J;
-    const int D = p.D;
+    const int D = DT <= 4 ? DT : p.D;  // instantiations up to 4 thresholds are exact: the threshold loops unroll without tests
     const int D2 = 2 * D;
     const float one_minus = 1.0f - CS_TIE_EPS, one_plus = 1.0f + CS_TIE_EPS;
     const float one_plus_tol = 1.0f + p.tol;
@@ -562,82 +562,80 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 const uint32_t k = V.k;
                 const uint2 dF = cs_ld(&A.ds[V.far]);
                 const uint32_t fid = V.far == J ? S.id : V.far;
-                // walk from F toward v: CS3_W(t) = distance of m_t via F (t = k .. 1), inf where not reached
-                for (uint32_t t = 1; t <= k; ++t) CS3_W(t) = __uint_as_float(INF);
-                if (dF.x != INF) {
-                    float b = __uint_as_float(dF.x);
-                    for (uint32_t t = 0; t < k; ++t) {
-                        const float nb2 = __fadd_rn(b, CS3_CB(V.sF + t));
-                        if (nb2 > p.max_seconds) break;
-                        if (nb2 == b) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
-                        b = nb2;
-                        CS3_W(k - t) = b;
+                // Both waves at once: my front starts at v, theirs at F; the smaller front advances (the settle order of
+                // the chain's nodes), until the fronts meet or neither may advance (cutoff, centrality.rs:1407).
+                const bool f_reached = dF.x != INF;
+                const bool wins = !f_reached || dF.y > lr || (dF.y == lr && j < V.paf);  // exact ties, shared pieces
+                float a = av, a_prev = av;                    // distance of m_T (v when T == 0) and of the node before it
+                float b = __uint_as_float(dF.x), b_prev = b;  // distance of m_{k+1-jn} (F when jn == 0) and the one before
+                float a_next = __fadd_rn(a, CS3_CB(V.sv));    // my candidate for m_{T+1}
+                float b_next = f_reached ? __fadd_rn(b, CS3_CB(V.sF)) : __uint_as_float(INF);  // theirs for m_{k-jn}
+                uint32_t T = 0, jn = 0;
+                while (T + jn < k) {
+                    const bool a_ok = !(a_next > p.max_seconds);
+                    const bool b_ok = f_reached && !(b_next > p.max_seconds);
+                    if (!a_ok && !b_ok) break;
+                    bool take_a = a_ok;
+                    if (a_ok && b_ok)  // the last unsettled node is claimed from both sides; otherwise two different nodes
+                        take_a = T + jn + 1 == k ? (a_next < b_next || (a_next == b_next && wins)) : a_next <= b_next;
+                    if (take_a) {
+                        if (a_next == a) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
+                        a_prev = a;
+                        a = a_next;
+                        ++T;
+                        if (p.closeness) {
+                            const int th = cs3_first_threshold<DT>(p, __fmul_rn(a, p.speed));
+                            atomicAdd(&histN[th], 1u);
+                            atomicAdd(&histE[th], 1u);  // piece (m_{T-1}, m_T): the larger cost is m_T's
+                        }
+                        a_next = __fadd_rn(a, CS3_CB(V.sv + T));
+                    } else {
+                        if (b_next == b) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
+                        b_prev = b;
+                        b = b_next;
+                        ++jn;
+                        b_next = __fadd_rn(b, CS3_CB(V.sF + jn));
                     }
                 }
-                // the neighbour on this link (m_1, or F itself) as a candidate predecessor of v
-                const uint32_t ud = k == 0 ? dF.x : __float_as_uint(CS3_W(1));
-                const uint32_t uid = k == 0 ? fid : V.id1;
+                n_interior += T;
+                // the neighbour on this link (m_1, or F itself) as a candidate predecessor of v: only when the wave from F
+                // took the whole chain; its candidate is the next step of that wave
                 uint32_t c_ud = INF;
                 float c_c = 0.f;
-                if (ud != INF && lr != 0) {
+                const uint32_t uid = k == 0 ? fid : V.id1;
+                if (f_reached && jn == k && lr != 0) {
+                    const uint32_t ud = __float_as_uint(b);
                     const bool before = k == 0 ? (dF.y < lr) : cs3_before(g, S, ud, uid, lavb, lvid);
-                    if (before) {
-                        const float c = __fadd_rn(__uint_as_float(ud), CS3_CB(V.sF + k));
-                        if (p.phase2 || !(c > p.max_seconds)) {
-                            c_ud = ud;
-                            c_c = c;
-                        }
+                    if (before && (p.phase2 || !(b_next > p.max_seconds))) {
+                        c_ud = ud;
+                        c_c = b_next;
                     }
                 }
                 s_cc[jl * 8 + j] = c_c;
                 s_cd[jl * 8 + j] = c_ud;
                 s_cu[jl * 8 + j] = uid | (V.paf << 28);
                 s_cr[jl * 8 + j] = dF.y;  // sigma of the neighbour = sigma of F (one-predecessor run)
-                // own side of the chain: m_1 .. m_T are reached from v first
-                const bool wins = dF.x == INF || dF.y > lr || (dF.y == lr && j < V.paf);  // exact ties, shared pieces
-                uint32_t T = 0;
-                float a = av, a_prev = av;  // a = distance of m_T (v when T == 0), a_prev that of m_{T-1}
-                for (uint32_t t = 1; t <= k; ++t) {
-                    const float na = __fadd_rn(a, CS3_CB(V.sv + t - 1));
-                    if (na > p.max_seconds) break;
-                    if (na == a) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
-                    const float bt = CS3_W(t);
-                    if (!(na < bt || (na == bt && wins))) break;
-                    a_prev = a;
-                    a = na;
-                    T = t;
-                    if (p.closeness) {
-                        const int th = cs3_first_threshold<DT>(p, __fmul_rn(na, p.speed));
-                        atomicAdd(&histN[th], 1u);
-                        atomicAdd(&histE[th], 1u);  // piece (m_{t-1}, m_t): the larger cost is m_t's
-                    }
-                }
-                n_interior += T;
                 uint32_t flags = 0;
-                // meeting pair X = m_T (v when T == 0), Y = m_{T+1} (F when T == k)
-                const uint32_t yd = T == k ? dF.x : __float_as_uint(CS3_W(T + 1));
-                if (yd != INF) {
-                    const float ydf = __uint_as_float(yd);
+                // meeting pair X = m_T (v when T == 0), Y = m_{T+1} (F when T == k): Y is reached iff the fronts met
+                if (f_reached && T + jn == k) {
+                    const uint32_t yd = __float_as_uint(b);
                     if (p.closeness && V.cnt && (dF.y > lr || (dF.y == lr && j < V.paf))) {
-                        const float ec = __fmul_rn(fmaxf(a, ydf), p.speed);
+                        const float ec = __fmul_rn(fmaxf(a, b), p.speed);
                         atomicAdd(&histE[cs3_first_threshold<DT>(p, ec)], V.cnt);
                     }
                     const uint32_t xid = T == 0 ? lvid : V.id1 + V.step * (int)(T - 1);
                     const uint32_t yid = T == k ? fid : V.id1 + V.step * (int)T;
                     const bool x_later = cs3_before(g, S, yd, yid, __float_as_uint(a), xid);
                     if (x_later && T >= 1) {
-                        // X has its own-side predecessor m_{T-1} and, perhaps, Y
-                        const float c_oth = __fadd_rn(ydf, CS3_CB(V.sF + (k - T)));
+                        // X has its own-side predecessor m_{T-1} and, perhaps, Y (candidate: the next step of their wave)
                         const uint32_t pid = T == 1 ? lvid : V.id1 + V.step * (int)(T - 2);
                         const bool own_first = cs3_before(g, S, __float_as_uint(a_prev), pid, yd, yid);
-                        if (cs3_other_kept(a, c_oth, own_first, p.phase2 != 0, one_plus_tol, p.max_seconds)) flags |= 0x10u;
+                        if (cs3_other_kept(a, b_next, own_first, p.phase2 != 0, one_plus_tol, p.max_seconds)) flags |= 0x10u;
                     } else if (!x_later && T < k) {
                         // Y (an interior on F's side) has its own predecessor m_{T+2} / F and, perhaps, X
-                        const float c_oth = __fadd_rn(a, CS3_CB(V.sv + T));
-                        const uint32_t qd = T + 1 == k ? dF.x : __float_as_uint(CS3_W(T + 2));
                         const uint32_t qid = T + 1 == k ? fid : V.id1 + V.step * (int)(T + 1);
-                        const bool own_first = cs3_before(g, S, qd, qid, __float_as_uint(a), xid);
-                        if (cs3_other_kept(ydf, c_oth, own_first, p.phase2 != 0, one_plus_tol, p.max_seconds)) flags |= 0x20u;
+                        const bool own_first = cs3_before(g, S, __float_as_uint(b_prev), qid, __float_as_uint(a), xid);
+                        if (cs3_other_kept(b, a_next, own_first, p.phase2 != 0, one_plus_tol, p.max_seconds)) flags |= 0x20u;
                     }
                 }
                 s_info[jl * 8 + j] = (uint8_t)(T | flags);
@@ -793,11 +791,10 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                     __syncwarp();
                     if (T) {
                         const CsView V = cs3_view(g, S, v, off, j);
-                        cs3_load_block(g, V, cblk, V.sv, T);
                         uint32_t pos = inc - T;
                         float a = av;
                         for (uint32_t t = 1; t <= T; ++t, ++pos) {
-                            a = __fadd_rn(a, CS3_CB(V.sv + t - 1));
+                            a = __fadd_rn(a, __ldg(&g.csec[V.blk + V.sv + t - 1]));
                             l_id[pos] = V.id1 + V.step * (int)(t - 1);
                             l_cost[pos] = __fmul_rn(a, p.speed);
                         }
@@ -903,9 +900,8 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                         } else if (yhas) {
                             // Y = m_{T+1} was reached from F but keeps m_T (or this junction) as a second predecessor:
                             // it is the last-settled node of the chain, so its dependency is its seed
-                            cs3_load_block(g, V, cblk, V.sF, k - T);
                             float b = __uint_as_float(dF.x);
-                            for (uint32_t t = 0; t < k - T; ++t) b = __fadd_rn(b, CS3_CB(V.sF + t));
+                            for (uint32_t t = 0; t < k - T; ++t) b = __fadd_rn(b, __ldg(&g.csec[V.blk + V.sF + t]));
                             const float cost_y = __fmul_rn(b, p.speed);
                             const uint32_t yid = V.id1 + V.step * (int)T;
                             const double pc = __ldg(&p.eligible[yid]) ? 0.5 : 1.0;
@@ -938,10 +934,9 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                         const uint32_t offs = tinc - T;
                         __syncwarp();
                         if (go && T) {
-                            cs3_load_block(g, V, cblk, V.sv, T);
                             float a = law;
                             for (uint32_t t = 1; t <= T; ++t) {
-                                a = __fadd_rn(a, CS3_CB(V.sv + t - 1));
+                                a = __fadd_rn(a, __ldg(&g.csec[V.blk + V.sv + t - 1]));
                                 s_ids[offs + t - 1] = V.id1 + V.step * (int)(t - 1);
                                 s_cst[offs + t - 1] = __fmul_rn(a, p.speed);
                             }
@@ -999,19 +994,18 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                                 }
                             }
                         }
-                        // outflow into the junction, link by link (ascending j: the reference's accumulation order)
-                        for (uint32_t sl = 0; sl < CS3_MAX_LINKS; ++sl) {
-                            if (go && j == sl) {
+                        // outflow into the junction (a handful of non-negative f64 terms per junction: the order of
+                        // the shared-memory atomics does not matter beyond the last bit)
+                        if (go) {
 #pragma unroll
-                                for (int i = 0; i < DT; ++i) {
-                                    if (i < D) {
-                                        s_acc[i * 32 + jl] += dl[i];
-                                        s_acc[(DT + i) * 32 + jl] += dlb[i];
-                                    }
+                            for (int i = 0; i < DT; ++i) {
+                                if (i < D) {
+                                    atomicAdd(&s_acc[i * 32 + jl], dl[i]);
+                                    atomicAdd(&s_acc[(DT + i) * 32 + jl], dlb[i]);
                                 }
                             }
-                            __syncwarp();
                         }
+                        __syncwarp();
                         remaining &= ~gom;
                     }
                 }

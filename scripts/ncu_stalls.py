@@ -39,7 +39,7 @@ for k in range(min(len(sass), len(lines))):
     r = sass[k]
     s = float(r[ci["# Samples"]] or 0)
     allsum += s
-    if not key or not key[0].startswith("cs_shortest2"):
+    if not key or not key[0].startswith(os.environ.get("SRCFILE", "cs_shortest2")):
         continue
     for nm, lo, hi_ in phases:
         if lo <= key[1] <= hi_:

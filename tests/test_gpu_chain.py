@@ -1,0 +1,163 @@
+"""GPU parity of the chain-contracted centrality_shortest kernel (cs_shortest3.cuh) on the graph shapes that stress its
+chain logic: sources inside chains, chains that loop back to their junction, interior-only rings, runs longer than the
+per-chain cap, parallel chains that tie, waves meeting inside a chain under the epsilon and the tolerance rule.
+Every case is checked against the CPU oracle on identical inputs: counts bit-exact, float metrics within 1e-5."""
+import numpy as np
+import pytest
+
+import helpers as H
+from cityseer_b200 import synth
+from cityseer_b200.rustalgos.centrality import validate_tolerance
+from cityseer_b200.tools import io
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture(autouse=True)
+def chain_kernel():
+    from cityseer_b200 import _native
+
+    _native.DEFAULT_OPTIONS["kernel"] = 3.0  # required: no silent fallback to another kernel
+    yield
+    _native.DEFAULT_OPTIONS.pop("kernel", None)
+
+
+def check(oracle_mod, ns, distances, **kw):
+    d, b, s = H.pair(distances=distances)
+    res = ns.centrality_shortest(distances=distances, pbar_disabled=True, **kw)
+    assert res.stats["kernel_used"] == 3
+    og = oracle_mod.OracleGraph(ns.frozen())
+    ref, cnt = og.centrality_shortest(d, b, s, H.SPEED, tol=validate_tolerance(kw.get("tolerance")), n_threads=8)
+    got = res._out
+    assert np.array_equal(got[0], ref[0]), "node_density not bit-exact"
+    assert np.array_equal(got[2], ref[2]), "node_cycles not bit-exact"
+    for m, name in enumerate(("density", "farness", "cycles", "harmonic", "beta", "betweenness", "betweenness_beta")):
+        np.testing.assert_allclose(got[m], ref[m], rtol=RTOL, atol=1e-7, err_msg=name)
+    for key in ("settled", "edge_iters", "sum_ri", "sum_ci"):
+        assert res.stats[key] == cnt[key], key
+    return res
+
+
+def polyline(points, step):
+    """Nodes every ~`step` metres along a polyline (slightly uneven, so that no two pieces are equal)."""
+    xy = [points[0]]
+    rng = np.random.default_rng(len(points) * 7919 + int(step))
+    for a, b in zip(points[:-1], points[1:]):
+        a, b = np.asarray(a, float), np.asarray(b, float)
+        n = max(1, int(np.ceil(np.linalg.norm(b - a) / step)))
+        ts = np.sort(np.concatenate([[1.0], (np.arange(1, n) + rng.uniform(-0.2, 0.2, n - 1)) / n])) if n > 1 else [1.0]
+        xy += [tuple(a + (b - a) * t) for t in ts]
+    return xy
+
+
+def build(paths, step=20.0):
+    """paths: list of point lists; shared end points (rounded coordinates) become shared nodes."""
+    coords, edges, key_of = {}, [], {}
+
+    def node(pt):
+        k = (round(pt[0], 6), round(pt[1], 6))
+        if k not in key_of:
+            key_of[k] = f"n{len(key_of)}"
+            coords[key_of[k]] = (float(pt[0]), float(pt[1]))
+        return key_of[k]
+
+    for pts in paths:
+        xy = polyline(pts, step)
+        for a, b in zip(xy[:-1], xy[1:]):
+            edges.append((node(a), node(b)))
+    g = H.graph_from_coords(coords, edges)
+    return io.network_structure_from_nx(g)[2]
+
+
+def test_long_path_is_cut_into_chains(oracle_mod):
+    ns = build([[(0, 0), (1500, 0)]])  # 75 pieces between two dead ends: runs are cut every 12 interiors
+    check(oracle_mod, ns, [200, 600, 1200])
+
+
+def test_interior_only_ring(oracle_mod):
+    c = [(300 * np.cos(t), 300 * np.sin(t)) for t in np.linspace(0, 2 * np.pi, 13)[:-1]]
+    ns = build([c + [c[0]]])  # no junction at all: every node has two neighbours
+    check(oracle_mod, ns, [300, 700, 1500])
+
+
+def test_loop_chain_on_a_stem(oracle_mod):
+    # a lollipop: the ring is one chain from the junction back to itself
+    ring = [(400 + 150 * np.cos(t), 150 * np.sin(t)) for t in np.linspace(np.pi, 3 * np.pi, 10)]
+    ns = build([[(0, 0), (250, 0)], ring])
+    check(oracle_mod, ns, [150, 400, 900])
+    check(oracle_mod, ns, [400, 900], tolerance=1.0)
+
+
+def test_parallel_chains_meet_inside(oracle_mod):
+    # three routes of nearly equal length between two junctions: the waves meet inside the chains
+    a, b = (0.0, 0.0), (600.0, 0.0)
+    ns = build([[a, (300, 40), b], [a, (300, -40.3), b], [a, (300, 120), b], [(-200, 0), a], [b, (800, 0)]])
+    check(oracle_mod, ns, [300, 600, 1200])
+    check(oracle_mod, ns, [300, 600, 1200], tolerance=0.5)
+    check(oracle_mod, ns, [600, 1200], tolerance=2.0)
+
+
+def test_symmetric_routes_tie_within_epsilon(oracle_mod):
+    # mirror-image routes: the two candidate distances at the meeting nodes agree to ~1e-6 relative (epsilon ties)
+    a, b = (0.0, 0.0), (500.0, 0.0)
+    up = [a, (100, 80), (400, 80), b]
+    dn = [a, (100, -80), (400, -80), b]
+    ns = build([up, dn, [(-150, 0), a], [b, (650, 0)]], step=25.0)
+    check(oracle_mod, ns, [250, 500, 1000])
+    check(oracle_mod, ns, [500, 1000], tolerance=1.0)
+
+
+@pytest.mark.parametrize("tolerance", [None, 0.3, 2.0])
+def test_decomposed_grid_with_tolerance(oracle_mod, tolerance):
+    ns, _ = synth.config("cfg4", 0.05)
+    kw = {} if tolerance is None else {"tolerance": tolerance}
+    check(oracle_mod, ns, [400, 800, 1600], **kw)
+
+
+def test_decomposed_grid_single_threshold_and_many(oracle_mod):
+    ns, _ = synth.config("cfg4", 0.04)
+    check(oracle_mod, ns, [700])
+    check(oracle_mod, ns, [200, 400, 600, 800, 1000])  # D = 5 runs the 8-threshold instantiation
+
+
+def test_source_subset_inside_chains(oracle_mod):
+    ns, _ = synth.config("cfg4", 0.05)
+    f = ns.frozen()
+    deg = np.bincount(f.src[f.edge_exists.astype(bool)], minlength=f.node_bound)
+    interior = np.flatnonzero(deg == 2)[::7][:200]
+    d, b, s = H.pair(distances=[500, 1000])
+    res = ns.centrality_shortest(distances=[500, 1000], source_indices=interior.tolist(), sample_probability=1.0, pbar_disabled=True)
+    assert res.stats["kernel_used"] == 3
+    og = oracle_mod.OracleGraph(f)
+    elig = np.zeros(f.node_bound, np.uint8)
+    elig[interior] = 1  # an explicit source list is the eligible set (centrality.rs:1032-1139)
+    ref, cnt = og.centrality_shortest(d, b, s, H.SPEED, sources=interior.astype(np.uint32),
+                                      wt=np.ones(len(interior), np.float32), eligible=elig, n_threads=8)  # fmt: skip
+    assert np.array_equal(res._out[0], ref[0]) and np.array_equal(res._out[2], ref[2])
+    np.testing.assert_allclose(res._out, ref, rtol=RTOL, atol=1e-7)
+    assert res.stats["settled"] == cnt["settled"] and res.stats["sum_ci"] == cnt["sum_ci"]
+
+
+def test_one_way_piece_uses_the_arena_kernel(oracle_mod):
+    # an edge without a twin disqualifies the graph for the chain kernel: "auto" serves it with the arena kernel,
+    # requiring the chain kernel fails loudly
+    from cityseer_b200 import _native
+    from cityseer_b200.rustalgos.graph import NetworkStructure
+
+    ns = NetworkStructure()
+    for i in range(6):
+        ns.add_street_node(f"k{i}", 100.0 * i, 0.0, True, 1.0)
+    for i in range(5):
+        ns.add_street_edge(i, i + 1, 0, f"k{i}", f"k{i + 1}", f"LINESTRING ({100.0 * i} 0, {100.0 * (i + 1)} 0)")
+        if i != 2:
+            ns.add_street_edge(i + 1, i, 0, f"k{i + 1}", f"k{i}", f"LINESTRING ({100.0 * (i + 1)} 0, {100.0 * i} 0)")
+    with pytest.raises(ValueError, match="chain-contracted kernel cannot serve"):
+        ns.centrality_shortest(distances=[300], pbar_disabled=True)
+    _native.DEFAULT_OPTIONS["kernel"] = 0.0
+    ns._invalidate()
+    res = ns.centrality_shortest(distances=[300], pbar_disabled=True)
+    assert res.stats["kernel_used"] == 1
+    d, b, s = H.pair(distances=[300])
+    ref, _ = oracle_mod.OracleGraph(ns.frozen()).centrality_shortest(d, b, s, H.SPEED, n_threads=2)
+    np.testing.assert_allclose(res._out, ref, rtol=RTOL, atol=1e-7)
