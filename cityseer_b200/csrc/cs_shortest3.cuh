@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
     const CsWarpArena A = cs_arena(p.arena, p.lay, worker);
     uint8_t* linfo = A.bdone;          // [rcap][8] link bytes: T | tie2 << 4 | yhas << 5
     uint32_t* minsucc = A.node_list;   // [rcap] after P2: smallest rank that has this junction as a predecessor
+    uint32_t* frank = reinterpret_cast<uint32_t*>(p.arena + (size_t)worker * p.lay.stride + p.lay.frank);  // [rcap][8]
+    uint32_t* needm = reinterpret_cast<uint32_t*>(p.arena + (size_t)worker * p.lay.stride + p.lay.needm);  // [rcap]
     const CsV3Graph& g = p.g;
     const uint32_t J = g.J;
     const int D = DT <= 4 ? DT : p.D;  // instantiations up to 4 thresholds are exact: the threshold loops unroll without tests
@@ -510,6 +512,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 cs_st(&A.ds[node].y, rank);
                 cs_st(&A.sigma[rank], 0.0);
                 cs_st(&minsucc[rank], CS_NOSLOT);  // (node_list is dead from here on)
+                cs_st(&needm[rank], 0u);
                 edge_iters += node == J ? 2u : (__ldg(&g.jinfo[node]).y >> 8);
             }
             __syncwarp();
@@ -615,6 +618,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 s_cd[jl * 8 + j] = c_ud;
                 s_cu[jl * 8 + j] = uid | (V.paf << 28);
                 s_cr[jl * 8 + j] = dF.y;  // sigma of the neighbour = sigma of F (one-predecessor run)
+                cs_st(&frank[(size_t)lr * 8 + j], dF.y);
                 uint32_t flags = 0;
                 // meeting pair X = m_T (v when T == 0), Y = m_{T+1} (F when T == k): Y is reached iff the fronts met
                 if (f_reached && T + jn == k) {
@@ -701,13 +705,11 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                         }
                     }
                 }
-                uint32_t amask = 0;
                 for (uint32_t mm = pmask_c; mm; mm &= mm - 1) {
                     const int q = __ffs(mm) - 1;
-                    amask |= 1u << (cj[q] & 0xffu);
                     atomicMin(&minsucc[crk[q]], r);  // P5 forms chunks whose junctions do not depend on each other
+                    atomicOr(&needm[crk[q]], 1u << (cj[q] >> 8));  // ... and that link of F carries this junction's dependency
                 }
-                cs_st(&A.predmask[r], amask);
                 if (r == 0) cs_st(&A.sigma[r], 1.0);
             }
             bool pending = valid && r != 0;
@@ -742,6 +744,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
 
         // ------------------------------------------------------------------ P4: closeness scatter to targets
         unsigned long long n_ri = 0, n_ci = 0;
+        uint32_t n_chunks = 0, n_batches = 0;
         if (p.closeness) {
             if (lane < (uint32_t)D) {
                 long long ncount = 0, ecount = 0;
@@ -791,12 +794,21 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                     __syncwarp();
                     if (T) {
                         const CsView V = cs3_view(g, S, v, off, j);
-                        uint32_t pos = inc - T;
+                        const uint32_t pos = inc - T;
                         float a = av;
-                        for (uint32_t t = 1; t <= T; ++t, ++pos) {
-                            a = __fadd_rn(a, __ldg(&g.csec[V.blk + V.sv + t - 1]));
-                            l_id[pos] = V.id1 + V.step * (int)(t - 1);
-                            l_cost[pos] = __fmul_rn(a, p.speed);
+                        const float* sec = g.csec + V.blk + V.sv;
+                        for (uint32_t t0 = 0; t0 < T; t0 += 4) {  // the loads of four pieces are in flight together
+                            float sx[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) sx[u] = t0 + u < T ? __ldg(sec + t0 + u) : 0.f;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (t0 + u < T) {
+                                    a = __fadd_rn(a, sx[u]);
+                                    l_id[pos + t0 + u] = V.id1 + V.step * (int)(t0 + u);
+                                    l_cost[pos + t0 + u] = __fmul_rn(a, p.speed);
+                                }
+                            }
                         }
                     }
                     __syncwarp();
@@ -818,19 +830,21 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
             const double wt_d = (double)wt;
             int hi = (int)R - 1;
             while (hi >= 0) {
+                ++n_chunks;
                 const int rr = hi - (int)lane;
                 const uint32_t ms = rr >= 0 ? cs_ld(&minsucc[rr]) : 0u;
                 const uint32_t badm = __ballot_sync(CS_FULL, rr < 0 || ms <= (uint32_t)hi);
                 const uint32_t cnt = badm ? (uint32_t)__ffs(badm) - 1u : 32u;  // >= 1: minsucc[hi] > hi
                 const bool valid = lane < cnt;
                 const uint32_t r = (uint32_t)(hi - (int)lane);
-                uint32_t w = 0, off = 0, deg = 0;
+                uint32_t w = 0, off = 0, deg = 0, nm = 0;
                 float aw = 0.f;
                 double sigma_w = 1.0;
                 if (valid) {
                     w = cs_ld(&A.s_node[r]);
                     aw = cs_ld(&A.s_agg[r]);
                     sigma_w = cs_ld(&A.sigma[r]);
+                    nm = cs_ld(&needm[r]);
                     deg = 2;
                     if (w != J) {
                         const uint2 ji = __ldg(&g.jinfo[w]);
@@ -855,6 +869,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 for (int i = 0; i < 2 * DT; ++i) s_acc[i * 32 + lane] = 0.0;
                 __syncwarp();
                 for (uint32_t base = 0; base < totalL; base += 32) {
+                    ++n_batches;
                     const uint32_t e = base + lane;
                     const bool act = e < totalL;
                     const uint32_t code = act ? s_llist[e] : 0u;
@@ -862,6 +877,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                     const uint32_t lw = __shfl_sync(CS_FULL, w, jl), loff = __shfl_sync(CS_FULL, off, jl);
                     const float law = __shfl_sync(CS_FULL, aw, jl);
                     const double lsig = __shfl_sync(CS_FULL, sigma_w, jl);
+                    const uint32_t lnm = __shfl_sync(CS_FULL, nm, jl);
                     const uint32_t lr = (uint32_t)(hi - (int)jl);
                     uint32_t T = 0;
                     bool tie2 = false, work = false;
@@ -877,19 +893,18 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                         T = ib & 15u;
                         tie2 = (ib & 0x10u) != 0;
                         const bool yhas = (ib & 0x20u) != 0;
-                        V = cs3_view(g, S, lw, loff, j);
-                        const uint32_t k = V.k;
-                        bool needF = false;
-                        uint2 dF = make_uint2(INF, CS_NOSLOT);
-                        if (T == k || yhas || tie2) dF = cs_ld(&A.ds[V.far]);
-                        if (T == k && dF.x != INF && dF.y > lr) needF = (cs_ld(&A.predmask[dF.y]) >> V.paf) & 1u;
+                        // F continues the path through this link iff F chose it as a predecessor (P3b left the bit)
+                        const bool needF = (lnm >> j) & 1u;
                         work = T > 0 || needF || yhas;
+                        const uint32_t rankF = (needF || yhas || tie2) ? cs_ld(&frank[(size_t)lr * 8 + j]) : 0u;
+                        if (work) V = cs3_view(g, S, lw, loff, j);
+                        const uint32_t k = V.k;
                         double sigma_F = 0.0;
-                        if (needF || yhas || tie2) sigma_F = cs_ld(&A.sigma[dF.y]);
+                        if (needF || yhas || tie2) sigma_F = cs_ld(&A.sigma[rankF]);
                         if (needF) {
                             // the whole chain is on this side and F continues the path (centrality.rs:861-866)
                             const double f = (sigma_F == lsig) ? 1.0 : lsig / sigma_F;
-                            const double* dx = A.dep + (size_t)dF.y * D2;
+                            const double* dx = A.dep + (size_t)rankF * D2;
 #pragma unroll
                             for (int i = 0; i < DT; ++i) {
                                 if (i < D) {
@@ -900,7 +915,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                         } else if (yhas) {
                             // Y = m_{T+1} was reached from F but keeps m_T (or this junction) as a second predecessor:
                             // it is the last-settled node of the chain, so its dependency is its seed
-                            float b = __uint_as_float(dF.x);
+                            float b = cs_ld(&A.s_agg[rankF]);
                             for (uint32_t t = 0; t < k - T; ++t) b = __fadd_rn(b, __ldg(&g.csec[V.blk + V.sF + t]));
                             const float cost_y = __fmul_rn(b, p.speed);
                             const uint32_t yid = V.id1 + V.step * (int)T;
@@ -935,10 +950,19 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                         __syncwarp();
                         if (go && T) {
                             float a = law;
-                            for (uint32_t t = 1; t <= T; ++t) {
-                                a = __fadd_rn(a, __ldg(&g.csec[V.blk + V.sv + t - 1]));
-                                s_ids[offs + t - 1] = V.id1 + V.step * (int)(t - 1);
-                                s_cst[offs + t - 1] = __fmul_rn(a, p.speed);
+                            const float* sec = g.csec + V.blk + V.sv;
+                            for (uint32_t t0 = 0; t0 < T; t0 += 4) {  // the loads of four pieces are in flight together
+                                float sx[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) sx[u] = t0 + u < T ? __ldg(sec + t0 + u) : 0.f;
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    if (t0 + u < T) {
+                                        a = __fadd_rn(a, sx[u]);
+                                        s_ids[offs + t0 + u] = V.id1 + V.step * (int)(t0 + u);
+                                        s_cst[offs + t0 + u] = __fmul_rn(a, p.speed);
+                                    }
+                                }
                             }
                         }
                         __syncwarp();
@@ -951,7 +975,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                                 s_pcs[en] = (float)pc;
 #pragma unroll
                                 for (int i = 0; i < DT; ++i)
-                                    if (i < D) s_crd[(2 * i + 1) * NB + en] = cost <= p.dist_f[i] ? pc * cs3_exp(-p.beta_d[i] * (double)cost) : 0.0;
+                                    if (i < D) s_crd[(2 * i + 1) * NB + en] = cost <= p.dist_f[i] ? pc * exp(-p.beta_d[i] * (double)cost) : 0.0;
                             }
                         }
                         __syncwarp();
@@ -1065,6 +1089,8 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
             atomicAdd(&p.counters[CS_C_PROGRESS], 1ull);
 #pragma unroll
             for (int k = 0; k < 6; ++k) atomicAdd(&p.counters[CS_C_PHASE0 + k], (unsigned long long)(tc[k + 1] - tc[k]));
+            atomicAdd(&p.counters[CS_C_PHASE0 + 6], (unsigned long long)n_chunks);   // dependency chunks
+            atomicAdd(&p.counters[CS_C_PHASE0 + 7], (unsigned long long)n_batches);  // 32-link batches
         }
     }
 #undef CS3_W
