@@ -197,7 +197,8 @@ def run_ours(args):
     out = torch.zeros((7, D, N), dtype=torch.float64, device=device)
     stream = torch.cuda.current_stream(device)
     dev.set_stream(stream.cuda_stream)
-    agg = {"settled": 0, "edge_iters": 0, "sum_ri": 0, "sum_ci": 0, "kernel_ms": 0.0, "launches": 0, "sources": 0}
+    agg = {"settled": 0, "edge_iters": 0, "sum_ri": 0, "sum_ci": 0, "kernel_ms": 0.0, "launches": 0, "sources": 0,
+           "kernel_used": 0}  # fmt: skip
 
     step_events = []
 
@@ -217,6 +218,7 @@ def run_ours(args):
                 agg[key] += st[key]
             agg["kernel_ms"] += st["kernel_ms"]
             agg["launches"] += st["gpu_launches"]
+            agg["kernel_used"] = st["kernel_used"]
         return st
 
     for k in range(args.warmup):
@@ -299,11 +301,12 @@ def run_ours(args):
             "config": {**info, "function": "centrality_shortest", "nodes": int(ns.node_count()),
                        "directed_edges": int(ns.edge_count), "distances_m": DISTANCES, "closeness": True,
                        "betweenness": True, "sources_per_step_per_gpu": batch, "parallelism": f"sources x{ws}",
-                       "l2": "per-step working set (per-warp distance maps + 172 MB of f64 outputs) exceeds the 126 MB L2; no flush"},
+                       "l2": "per-step working set (per-warp search arenas + 172 MB of f64 accumulators) exceeds the 126 MB L2; no flush"},
             "gteps": total_edges / (span_ms_max / 1e3) / 1e9,
             "kernel_ms_per_step": dev_ms_max / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_kind, "kernel": "cs_k_shortest",
+                         "traffic": traffic, "peak_source": peak_kind,
+                         "kernel": {1: "cs_k_shortest", 2: "cs_k_shortest2", 3: "cs_k_shortest3"}.get(agg["kernel_used"], "?"),
                          "algorithmic_bytes_per_source": alg_bytes(agg) / max(1, agg["sources"])},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "sources/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -55,7 +55,11 @@ template <class T>
 __device__ __forceinline__ void cs_st(T* p, T v) { __stcg(p, v); }
 
 __device__ __forceinline__ void cs_red_add(double* p, double v) {
+#ifdef CS_EXPERIMENT_NO_RED  // measurement only: how much of the time the f64 scatter costs
+    if (v == -1.2345) *p = v;
+#else
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+#endif
 }
 __device__ __forceinline__ unsigned long long cs_warp_sum(unsigned long long v) {
 #pragma unroll
