@@ -58,6 +58,8 @@ _f64p = C.POINTER(C.c_double)
 SIGNATURES = {
     "cs_last_error": (C.c_char_p, []),
     "cs_device_count": (C.c_int, []),
+    "cs_host_alloc": (C.c_void_p, [C.c_uint64]),
+    "cs_host_free": (None, [C.c_void_p]),
     "cs_graph_create": (
         C.c_void_p,
         [C.c_uint32, _u8p, _u8p, _f32p, _f64p, _f64p, _f64p, C.c_uint64, _u8p, _u32p, _u32p, _u32p, _f32p, _f32p, _f32p, _f32p, _i32p,
@@ -106,6 +108,21 @@ def load_library():
             fn.argtypes = args
         _lib = lib
         return lib
+
+
+def pinned_empty(lib, shape, dtype=np.float64) -> np.ndarray:
+    """A numpy array over a page-locked buffer from the library's pool (cs_host_alloc); the buffer returns to the pool
+    when the array (and every view of it) is garbage-collected.  Device-to-host copies into it run at full PCIe rate."""
+    import weakref
+
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = lib.cs_host_alloc(max(nbytes, 8))
+    if not ptr:
+        raise MemoryError(_err(lib))
+    buf = (C.c_uint8 * max(nbytes, 8)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib.cs_host_free, C.c_void_p(ptr))
+    return arr
 
 
 def _err(lib) -> str:
@@ -268,7 +285,7 @@ class DeviceGraph:
         D, da, ba, sa = self._thresholds(d, b, s)
         st = CsStats()
         if out_device_ptr is None:
-            out = np.empty((7, D, self.node_bound), dtype=np.float64)
+            out = pinned_empty(self._lib, (7, D, self.node_bound))
             optr, on_dev = out.ctypes.data_as(C.c_void_p), 0
         else:
             out, optr, on_dev = None, C.c_void_p(int(out_device_ptr)), 1
@@ -291,7 +308,7 @@ class DeviceGraph:
         D, da, _ba, sa = self._thresholds(d, None, s)
         st = CsStats()
         if out_device_ptr is None:
-            out = np.empty((4, D, self.node_bound), dtype=np.float64)
+            out = pinned_empty(self._lib, (4, D, self.node_bound))
             optr, on_dev = out.ctypes.data_as(C.c_void_p), 0
         else:
             out, optr, on_dev = None, C.c_void_p(int(out_device_ptr)), 1
@@ -311,7 +328,7 @@ class DeviceGraph:
         D, da, ba, sa = self._thresholds(d, b, s)
         st = CsStats()
         if out_device_ptr is None:
-            out = np.empty((4, D, self.node_bound), dtype=np.float64)
+            out = pinned_empty(self._lib, (4, D, self.node_bound))
             optr, on_dev = out.ctypes.data_as(C.c_void_p), 0
         else:
             out, optr, on_dev = None, C.c_void_p(int(out_device_ptr)), 1

@@ -144,6 +144,55 @@ extern "C" int cs_device_count(void) {
     return n;
 }
 
+// ------------------------------------------------------------------------------------------------ pinned result buffers
+static std::mutex g_pool_mu;
+static std::vector<std::pair<void*, uint64_t>> g_pool_free;  // (ptr, bytes), at most a handful
+static std::vector<std::pair<void*, uint64_t>> g_pool_live;
+
+extern "C" void* cs_host_alloc(uint64_t bytes) {
+    if (bytes == 0) bytes = 8;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_pool_free.size(); ++i) {
+        if (g_pool_free[i].second == bytes) {
+            void* p = g_pool_free[i].first;
+            g_pool_live.push_back(g_pool_free[i]);
+            g_pool_free.erase(g_pool_free.begin() + i);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        // make room: drop the cached buffers and retry once
+        for (auto& f : g_pool_free) cudaFreeHost(f.first);
+        g_pool_free.clear();
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            cs_fail("cudaHostAlloc of %llu bytes failed", (unsigned long long)bytes);
+            return nullptr;
+        }
+    }
+    g_pool_live.push_back({p, bytes});
+    return p;
+}
+
+extern "C" void cs_host_free(void* ptr) {
+    if (!ptr) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_pool_live.size(); ++i) {
+        if (g_pool_live[i].first == ptr) {
+            auto e = g_pool_live[i];
+            g_pool_live.erase(g_pool_live.begin() + i);
+            if (g_pool_free.size() < 4) {
+                g_pool_free.push_back(e);
+            } else {
+                cudaFreeHost(e.first);
+            }
+            return;
+        }
+    }
+}
+
 // Tobler slope penalty and the numerator of edge_travel_seconds, evaluated in f32 left to right exactly as
 // centrality.rs:969-1007: (length * imp * slope_pen) / speed.  The division by the per-call speed happens on device.
 static inline float slope_penalty(const double* z, uint32_t from, uint32_t to, float length_2d) {

@@ -34,12 +34,16 @@ class _ResultBase:
 
     def __init__(self, distances, node_keys_py, node_indices, out, stats):
         self.distances = [int(d) for d in distances]
-        self.node_keys_py = list(node_keys_py)
+        self._node_keys = node_keys_py  # shared with the graph, never mutated
         self._node_indices = np.asarray(node_indices, dtype=np.int64)
         self._out = out  # float64 [M][D][node_bound]
         self.stats = stats  # device counters / timings (extension; not part of the reference surface)
         self.reachability_totals: list[int] = []
         self.sampled_source_count: int = 0
+
+    @property
+    def node_keys_py(self) -> list:
+        return list(self._node_keys)
 
     @property
     def node_indices(self) -> list[int]:

@@ -198,6 +198,7 @@ class NetworkStructure:
         self._frozen: FrozenGraph | None = None
         self._bulk: FrozenGraph | None = None  # set by from_arrays(); immutable bulk-ingested graph
         self._bulk_keys = None
+        self._keys_cache = None
         self._device = None  # _native.DeviceGraph
         self._lock = threading.Lock()
 
@@ -220,6 +221,7 @@ class NetworkStructure:
         if self._bulk is not None:
             raise ValueError("NetworkStructure built with from_arrays() is immutable.")
         self._frozen = None
+        self._keys_cache = None
         if self._device is not None:
             self._device.close()
             self._device = None
@@ -326,11 +328,17 @@ class NetworkStructure:
         return self.node_indices()
 
     def node_keys_py(self) -> list[Any]:
-        if self._bulk is not None:
-            if self._bulk_keys is None:
-                return self._bulk.node_indices.tolist()
-            return list(self._bulk_keys)
-        return [p.node_key for p in self._nodes if p is not None]
+        return list(self._node_keys_shared())
+
+    def _node_keys_shared(self) -> list[Any]:
+        """The key list, built once per graph state and shared (read-only) by the result objects: rebuilding a
+        million-element Python list per call costs more than the GPU spends on small runs."""
+        if self._keys_cache is None:
+            if self._bulk is not None:
+                self._keys_cache = self._bulk.node_indices.tolist() if self._bulk_keys is None else list(self._bulk_keys)
+            else:
+                self._keys_cache = [p.node_key for p in self._nodes if p is not None]
+        return self._keys_cache
 
     @property
     def node_xs(self) -> list[float]:
@@ -741,7 +749,7 @@ class NetworkStructure:
         if compute_betweenness and scale != 1.0:
             out[5:7] *= scale
         f = self.frozen()
-        res = _centrality.CentralityShortestResult(d, self.node_keys_py(), f.node_indices, out, stats)
+        res = _centrality.CentralityShortestResult(d, self._node_keys_shared(), f.node_indices, out, stats)
         if tracked:
             res.sampled_source_count = int(len(sources))
             res.reachability_totals = [int(x) for x in stats["reach_totals"]] if compute_closeness else [0] * len(d)
@@ -796,7 +804,7 @@ class NetworkStructure:
         if compute_betweenness and scale != 1.0:
             out[3:4] *= scale
         f = self.frozen()
-        res = _centrality.CentralitySimplestResult(d, self.node_keys_py(), f.node_indices, out, stats)
+        res = _centrality.CentralitySimplestResult(d, self._node_keys_shared(), f.node_indices, out, stats)
         if tracked:
             res.sampled_source_count = int(len(sources))
             res.reachability_totals = [int(x) for x in stats["reach_totals"]] if compute_closeness else [0] * len(d)
@@ -834,7 +842,7 @@ class NetworkStructure:
             d, b, s, speed, compute_closeness, compute_betweenness, sources,
             None if pbar_disabled else self._progress, len(node_indices),
         )  # fmt: skip
-        return _centrality.CentralitySegmentResult(d, self.node_keys_py(), f.node_indices, out, stats)
+        return _centrality.CentralitySegmentResult(d, self._node_keys_shared(), f.node_indices, out, stats)
 
     # ------------------------------------------------------------------ single-source tree searches
     def _validate_dijkstra_inputs(self, src_idx: int, speed_m_s: float) -> None:

@@ -51,6 +51,12 @@ typedef struct cs_stats {
 const char* cs_last_error(void);
 int cs_device_count(void);
 
+/* Page-locked host buffers for results (the reference hands back numpy arrays it owns, common.rs:40-53; here the
+ * [M][D][node_bound] result is downloaded straight into page-locked memory at full PCIe rate).  Freed buffers return
+ * to a small pool and are reused by later calls of the same size.  `cs_host_alloc` returns NULL on failure. */
+void* cs_host_alloc(uint64_t bytes);
+void cs_host_free(void* ptr);
+
 /* Replaces NetworkStructure construction + add_street_node / add_street_edge ingest (graph.rs:427-452, :728-889) and
  * validate() (:1035-1058): takes the container's payload fields as flat arrays, builds both CSR orientations with
  * 16-byte edge records in petgraph adjacency order (newest edge first), uploads once to `device`.
