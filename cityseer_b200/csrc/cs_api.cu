@@ -549,7 +549,7 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
     rcap = std::max(rcap, 32u);
     const uint32_t qcap = rcap * 2 + 64;
     uint32_t workers = g->cfg_workers ? g->cfg_workers
-                                      : (uint32_t)g->sm_count * (kind == 3 ? CS3_MIN_BLOCKS : CS_MIN_BLOCKS) * CS_WARPS_PER_CTA;
+                                      : (uint32_t)g->sm_count * (kind == 3 ? CS3_MIN_BLOCKS * CS3_WARPS : CS_MIN_BLOCKS * CS_WARPS_PER_CTA);
     workers = std::max<uint32_t>(CS_WARPS_PER_CTA, workers / CS_WARPS_PER_CTA * CS_WARPS_PER_CTA);
     CsArenaLayout L{};
     size_t off = 0;

@@ -16,7 +16,9 @@
 
 #define CS3_KMAX 12       // interiors per chain (longer runs are cut at upload)
 #define CS3_MAX_LINKS 8   // links per junction
+#ifndef CS3_WARPS
 #define CS3_WARPS 8
+#endif
 #ifndef CS3_MIN_BLOCKS
 #define CS3_MIN_BLOCKS 2
 #endif
@@ -524,7 +526,33 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
         // P3a, one lane per LINK of the chunk's junctions: walk the chain from both ends, decide which interiors belong
         // to this end, evaluate the meeting pair, and leave the link's candidate predecessor of the junction in shared
         // memory.  P3b, one lane per junction: the reference's sequential rule over its candidates, then sigma.
+        // circuit-rank counts per threshold bin, 16 bits per bin in registers (up to three thresholds), flushed to the
+        // shared-memory histograms before any lane can overflow
+        unsigned long long cntN = 0, cntNE = 0, cntE = 0;
+        auto flush_counts = [&]() {
+            if constexpr (DT <= 3) {
+#pragma unroll
+                for (int b = 0; b <= DT; ++b) {
+                    uint32_t cn = (uint32_t)(cntN >> (16 * b)) & 0xffffu, cne = (uint32_t)(cntNE >> (16 * b)) & 0xffffu;
+                    uint32_t ce = (uint32_t)(cntE >> (16 * b)) & 0xffffu;
+                    cn += cne;
+                    ce += cne;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        cn += __shfl_xor_sync(CS_FULL, cn, o);
+                        ce += __shfl_xor_sync(CS_FULL, ce, o);
+                    }
+                    if (lane == 0) {
+                        histN[b] += cn;
+                        histE[b] += ce;
+                    }
+                }
+                cntN = cntNE = cntE = 0;
+                __syncwarp();
+            }
+        };
         for (uint32_t b0 = 0; b0 < R; b0 += 32) {
+            if ((b0 & (128u * 32u - 1u)) == 128u * 32u - 32u) flush_counts();
             const uint32_t r = b0 + lane;
             const bool valid = r < R;
             uint32_t v = 0, off = 0, deg = 0, vid = 0, avb = 0;
@@ -532,7 +560,11 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 v = cs_ld(&A.s_node[r]);
                 vid = v == J ? S.id : v;
                 avb = __float_as_uint(cs_ld(&A.s_agg[r]));
-                if (p.closeness) atomicAdd(&histN[cs3_first_threshold<DT>(p, __fmul_rn(__uint_as_float(avb), p.speed))], 1u);
+                if (p.closeness) {
+                    const int th = cs3_first_threshold<DT>(p, __fmul_rn(__uint_as_float(avb), p.speed));
+                    if constexpr (DT <= 3) cntN += 1ull << (16 * th);
+                    else atomicAdd(&histN[th], 1u);
+                }
                 deg = 2;
                 if (v != J) {
                     const uint2 ji = __ldg(&g.jinfo[v]);
@@ -588,8 +620,13 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                         ++T;
                         if (p.closeness) {
                             const int th = cs3_first_threshold<DT>(p, __fmul_rn(a, p.speed));
-                            atomicAdd(&histN[th], 1u);
-                            atomicAdd(&histE[th], 1u);  // piece (m_{T-1}, m_T): the larger cost is m_T's
+                            // a node and the piece (m_{T-1}, m_T), whose larger cost is m_T's
+                            if constexpr (DT <= 3) {
+                                cntNE += 1ull << (16 * th);
+                            } else {
+                                atomicAdd(&histN[th], 1u);
+                                atomicAdd(&histE[th], 1u);
+                            }
                         }
                         a_next = __fadd_rn(a, CS3_CB(V.sv + T));
                     } else {
@@ -625,7 +662,9 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                     const uint32_t yd = __float_as_uint(b);
                     if (p.closeness && V.cnt && (dF.y > lr || (dF.y == lr && j < V.paf))) {
                         const float ec = __fmul_rn(fmaxf(a, b), p.speed);
-                        atomicAdd(&histE[cs3_first_threshold<DT>(p, ec)], V.cnt);
+                        const int th = cs3_first_threshold<DT>(p, ec);
+                        if constexpr (DT <= 3) cntE += (unsigned long long)V.cnt << (16 * th);
+                        else atomicAdd(&histE[th], V.cnt);
                     }
                     const uint32_t xid = T == 0 ? lvid : V.id1 + V.step * (int)(T - 1);
                     const uint32_t yid = T == k ? fid : V.id1 + V.step * (int)T;
@@ -738,6 +777,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 if (!__any_sync(CS_FULL, pending)) break;
             }
         }
+        flush_counts();
         __syncwarp();
         tc[3] = clock64();
         CS3_BAR();
