@@ -1008,6 +1008,8 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
             t.beta_f[i] = p.beta_f[i];
             t.beta_d[i] = p.beta_d[i];
         }
+        t.beta_chain = D > 1;
+        for (int i = 0; i + 1 < D; ++i) t.beta_chain = t.beta_chain && (t.beta_d[i] == 2.0 * t.beta_d[i + 1]) && t.beta_d[i] > 0.0;
         t.max_seconds = p.max_seconds;
         t.speed = speed;
         t.tol = tol;

@@ -42,6 +42,7 @@ struct CsV3Graph {
 struct CsShortest3Params {
     CsV3Graph g;
     int D, closeness, betweenness, phase2;
+    int beta_chain;  // every beta is exactly twice the next one (distances that double): one exp, then squarings
     float dist_f[CS_MAX_THRESHOLDS];
     float beta_f[CS_MAX_THRESHOLDS];
     double beta_d[CS_MAX_THRESHOLDS];
@@ -1013,9 +1014,22 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                                 const float cost = s_cst[en];
                                 const double pc = __ldg(&p.eligible[s_ids[en]]) ? 0.5 : 1.0;
                                 s_pcs[en] = (float)pc;
+                                if (p.beta_chain) {
+                                    // beta_i = 2 * beta_{i+1} exactly (e.g. 500 / 1000 / 2000 m): exp(-beta_i c) is the square
+                                    // of exp(-beta_{i+1} c) to within an ulp or two
+                                    double ex = exp(-p.beta_d[D - 1] * (double)cost);
 #pragma unroll
-                                for (int i = 0; i < DT; ++i)
-                                    if (i < D) s_crd[(2 * i + 1) * NB + en] = cost <= p.dist_f[i] ? pc * exp(-p.beta_d[i] * (double)cost) : 0.0;
+                                    for (int i = DT - 1; i >= 0; --i) {
+                                        if (i < D) {
+                                            s_crd[(2 * i + 1) * NB + en] = cost <= p.dist_f[i] ? pc * ex : 0.0;
+                                            ex *= ex;
+                                        }
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < DT; ++i)
+                                        if (i < D) s_crd[(2 * i + 1) * NB + en] = cost <= p.dist_f[i] ? pc * cs3_exp(-p.beta_d[i] * (double)cost) : 0.0;
+                                }
                             }
                         }
                         __syncwarp();
