@@ -85,6 +85,11 @@ SIGNATURES = {
         [C.c_void_p, C.c_int, _u32p, _f32p, _u32p, C.c_float, C.c_int, C.c_int, C.c_uint64, _u32p, C.c_void_p, C.c_int,
          C.c_int, C.POINTER(CsStats)],
     ),  # fmt: skip
+    "cs_betweenness_od_shortest": (
+        C.c_int,
+        [C.c_void_p, C.c_int, _u32p, _f32p, _u32p, C.c_float, C.c_float, C.c_uint64, _u32p, _u64p, _u32p, _f32p,
+         C.c_void_p, C.c_int, C.POINTER(CsStats)],
+    ),  # fmt: skip
     "cs_progress": (C.c_uint64, [C.c_void_p]),
     "cs_shortest_search": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _f32p, _f64p, _u32p]),
 }
@@ -301,6 +306,26 @@ class DeviceGraph:
             )  # fmt: skip
 
         self._run(call, progress, n_prog, n_src)
+        return out, self._stats(st, D)
+
+    def betweenness_od_shortest(self, d, b, s, speed, tol, sources, od_off, od_dst, od_w, progress, n_prog):
+        """Returns float64 [7][D][node_bound] (rows 5, 6 populated) and the device counters."""
+        D, da, ba, sa = self._thresholds(d, b, s)
+        st = CsStats()
+        out = pinned_empty(self._lib, (7, D, self.node_bound))
+        sources = np.ascontiguousarray(sources, np.uint32)
+        od_off = np.ascontiguousarray(od_off, np.uint64)
+        od_dst = np.ascontiguousarray(od_dst, np.uint32)
+        od_w = np.ascontiguousarray(od_w, np.float32)
+
+        def call():
+            return self._lib.cs_betweenness_od_shortest(
+                self._h, D, _ptr(da, _u32p), _ptr(ba, _f32p), _ptr(sa, _u32p), speed, tol, len(sources),
+                _ptr(sources, _u32p), _ptr(od_off, _u64p), _ptr(od_dst, _u32p), _ptr(od_w, _f32p),
+                out.ctypes.data_as(C.c_void_p), 0, C.byref(st),
+            )  # fmt: skip
+
+        self._run(call, progress, n_prog, len(sources))
         return out, self._stats(st, D)
 
     def centrality_simplest(self, d, s, speed, tol, unit, offset, closeness, betweenness, sources, wt, eligible, progress,

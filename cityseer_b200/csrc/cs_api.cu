@@ -118,6 +118,11 @@ struct cs_graph {
     uint32_t *d3_int_chain = nullptr, *d3_orig_of_new = nullptr, *d3_new_of_orig = nullptr;
     uint8_t* d3_eligible = nullptr;
     float cached_speed3 = -1.f;
+    // OD betweenness: per-call destination lists on the device
+    unsigned long long* d_od_off = nullptr;
+    uint32_t* d_od_dst = nullptr;
+    float* d_od_w = nullptr;
+    size_t od_off_cap = 0, od_pairs_cap = 0;
     int last_kernel = 1;
     int opt_kernel = 0;  // 0 auto (chain-contracted kernel when the graph qualifies, else the global-arena kernel),
                          // 1 global-arena kernel, 2 shared-memory kernel, 3 chain-contracted kernel (required)
@@ -470,7 +475,8 @@ extern "C" void cs_graph_destroy(cs_graph* g) {
                     (void*)g->d_src_wt2, (void*)g->d_fb_wt, (void*)g->d_eligible2, g->d_cub_tmp, (void*)g->d_scratch2,
                     (void*)g->d_fb2_sources, (void*)g->d_fb2_wt, (void*)g->d3_jinfo, (void*)g->d3_links, (void*)g->d3_ctab,
                     (void*)g->d3_cnum, (void*)g->d3_csec, (void*)g->d3_weight, (void*)g->d3_int_chain,
-                    (void*)g->d3_orig_of_new, (void*)g->d3_new_of_orig, (void*)g->d3_eligible})
+                    (void*)g->d3_orig_of_new, (void*)g->d3_new_of_orig, (void*)g->d3_eligible, (void*)g->d_od_off,
+                    (void*)g->d_od_dst, (void*)g->d_od_w})
         if (p) cudaFree(p);
     if (g->h_progress) cudaFreeHost(g->h_progress);
     for (auto& e : g->ev)
@@ -839,7 +845,8 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
                         float speed, float tol, int closeness, int betweenness, uint64_t n_sources,
                         const uint32_t* sources, const float* source_wt, const uint8_t* eligible, double* out,
                         int out_on_device, int accumulate, cs_stats* stats, float* dump_agg, double* dump_sigma,
-                        uint32_t* dump_npred) {
+                        uint32_t* dump_npred, const uint64_t* od_off = nullptr, const uint32_t* od_dst = nullptr,
+                        const float* od_w = nullptr) {
     if (!g) return cs_fail("null graph");
     if (check_thresholds(D, seconds)) return 1;
     if (!closeness && !betweenness)
@@ -950,6 +957,34 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
     p.dump_agg = dump_agg;
     p.dump_sigma = dump_sigma;
     p.dump_npred = dump_npred;
+    if (od_off) {
+        const size_t n_pairs = (size_t)od_off[n_sources];
+        if (g->od_off_cap < n_sources + 1) {
+            if (g->d_od_off) cudaFree(g->d_od_off);
+            g->d_od_off = nullptr;
+            CS_CUDA(cudaMalloc(&g->d_od_off, (n_sources + 1) * sizeof(unsigned long long)));
+            g->od_off_cap = n_sources + 1;
+        }
+        if (g->od_pairs_cap < std::max<size_t>(n_pairs, 1)) {
+            if (g->d_od_dst) cudaFree(g->d_od_dst);
+            if (g->d_od_w) cudaFree(g->d_od_w);
+            g->d_od_dst = nullptr;
+            g->d_od_w = nullptr;
+            CS_CUDA(cudaMalloc(&g->d_od_dst, std::max<size_t>(n_pairs, 1) * 4));
+            CS_CUDA(cudaMalloc(&g->d_od_w, std::max<size_t>(n_pairs, 1) * 4));
+            g->od_pairs_cap = std::max<size_t>(n_pairs, 1);
+        }
+        for (size_t j = 0; j < n_pairs; ++j)
+            if (od_dst[j] >= g->n) return cs_fail("OD destination %u is out of range for node_bound %u", od_dst[j], g->n);
+        CS_CUDA(cudaMemcpyAsync(g->d_od_off, od_off, (n_sources + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, g->stream));
+        if (n_pairs) {
+            CS_CUDA(cudaMemcpyAsync(g->d_od_dst, od_dst, n_pairs * 4, cudaMemcpyHostToDevice, g->stream));
+            CS_CUDA(cudaMemcpyAsync(g->d_od_w, od_w, n_pairs * 4, cudaMemcpyHostToDevice, g->stream));
+        }
+        p.od_off = g->d_od_off;
+        p.od_dst = g->d_od_dst;
+        p.od_w = g->d_od_w;
+    }
     auto launch_v1 = [&](uint64_t m) -> int {
         if (ensure_arena(g, 0, D)) return 1;
         if (prep_seconds(g, speed, false, &launches)) return 1;
@@ -972,7 +1007,7 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
 
 
     // ---- chain-contracted kernel (cs_shortest3.cuh): junction-level search, chains walked in place
-    const bool dumping = dump_agg || dump_sigma || dump_npred;
+    const bool dumping = dump_agg || dump_sigma || dump_npred || od_off;  // served by the arena kernel
     bool use_v3 = !use_v2 && !dumping && g->v3_ok && n_sources > 0 && (g->opt_kernel == 3 || g->opt_kernel == 0);
     if (g->opt_kernel == 3 && !use_v3 && !dumping && n_sources > 0)
         return cs_fail("the chain-contracted kernel cannot serve this graph (an edge without a mutual twin, or a junction "
@@ -1137,6 +1172,19 @@ extern "C" int cs_centrality_shortest(cs_graph* g, int D, const uint32_t* distan
     return run_shortest(g, D, distances, betas, seconds, speed_m_s, tolerance, compute_closeness, compute_betweenness,
                         n_sources, sources, source_wt, eligible, out, out_on_device, accumulate, stats, nullptr, nullptr,
                         nullptr);
+}
+
+// betweenness_od_shortest (centrality.rs:2419-2540).  `out` is the [7][D][node_bound] layout of centrality_shortest with
+// only rows 5 (betweenness) and 6 (betweenness_beta) populated.
+extern "C" int cs_betweenness_od_shortest(cs_graph* g, int D, const uint32_t* distances, const float* betas,
+                                          const uint32_t* seconds, float speed_m_s, float tolerance, uint64_t n_sources,
+                                          const uint32_t* sources, const uint64_t* od_off, const uint32_t* od_dst,
+                                          const float* od_w, double* out, int out_on_device, cs_stats* stats) {
+    if (!out) return cs_fail("null output");
+    if (!sources || !od_off || (od_off[n_sources] && (!od_dst || !od_w))) return cs_fail("null OD arrays");
+    std::vector<float> ones(std::max<uint64_t>(n_sources, 1), 1.0f);
+    return run_shortest(g, D, distances, betas, seconds, speed_m_s, tolerance, 0, 1, n_sources, sources, ones.data(), nullptr,
+                        out, out_on_device, 0, stats, nullptr, nullptr, nullptr, od_off, od_dst, od_w);
 }
 
 extern "C" int cs_shortest_search(cs_graph* g, uint32_t src, uint32_t max_seconds, float speed_m_s, float tolerance,

@@ -34,6 +34,11 @@ struct CsShortestParams {
     float* dump_agg;  // optional per-node dumps (single-source debug search)
     double* dump_sigma;
     uint32_t* dump_npred;
+    // betweenness_od_shortest (centrality.rs:2419-2540): seeds only at the OD destinations of each source; the
+    // destinations / weights of sources[k] are od_dst / od_w [od_off[k], od_off[k + 1]); NULL for plain centrality
+    const unsigned long long* od_off;
+    const uint32_t* od_dst;
+    const float* od_w;
 };
 
 #ifndef CS_MIN_BLOCKS
@@ -286,6 +291,16 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
 
         // ------------------------------------------------------------------ P5: dependencies, reverse settle order
         tc[4] = clock64();
+        double* odw = reinterpret_cast<double*>(A.far);  // per-rank OD weight (the far queue is dead after the search)
+        if (p.od_off) {
+            for (uint32_t r = lane; r < R; r += 32) cs_st(&odw[r], 0.0);
+            __syncwarp();
+            for (unsigned long long j = __ldg(&p.od_off[si]) + lane; j < __ldg(&p.od_off[si + 1]); j += 32) {
+                const uint2 dd = cs_ld(&A.ds[__ldg(&p.od_dst[j])]);
+                if (dd.x != CS_INF_BITS) cs_st(&odw[dd.y], (double)__ldg(&p.od_w[j]));  // destinations are unique per origin
+            }
+            __syncwarp();
+        }
         if (p.betweenness) {
             const double wt_d = (double)wt;
             for (int b0 = (int)((R - 1) & ~31u); b0 >= 0; b0 -= 32) {
@@ -340,7 +355,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
                                 }
                             }
                             const bool is_src = (w == src);
-                            const double pc = is_src ? 0.0 : (__ldg(&p.eligible[w]) ? 0.5 : 1.0);
+                            const double pc = is_src ? 0.0 : p.od_off ? cs_ld(&odw[r]) : (__ldg(&p.eligible[w]) ? 0.5 : 1.0);
                             double* dr = A.dep + (size_t)r * D2;
 #pragma unroll
                             for (int i = 0; i < DT; ++i) {

@@ -152,6 +152,22 @@ def segment_centrality(network_structure, nodes_gdf, distances=None, betas=None,
     return _write(nodes_gdf, temp_data, result.node_keys_py)
 
 
+def betweenness_od(network_structure, nodes_gdf, od_matrix, distances=None, betas=None, minutes=None,
+                   min_threshold_wt: float = MIN_THRESH_WT, speed_m_s: float = SPEED_M_S, tolerance=None):  # fmt: skip
+    """OD-weighted betweenness (networks.py:383-461): only origins with outbound trips are searched, every shortest
+    path contribution is scaled by its OD weight; writes ``cc_betweenness_{d}`` / ``cc_betweenness_beta_{d}``."""
+    logger.info("Computing OD-weighted betweenness centrality.")
+    fn = partial(network_structure.betweenness_od_shortest, od_matrix=od_matrix, distances=distances, betas=betas,
+                 minutes=minutes, min_threshold_wt=min_threshold_wt, speed_m_s=speed_m_s, tolerance=tolerance)  # fmt: skip
+    result = config.wrap_progress(total=network_structure.street_node_count(), rust_struct=network_structure, partial_func=fn)
+    resolved, _b, _s = rustalgos.pair_distances_betas_time(speed_m_s, distances, betas, minutes, min_threshold_wt)
+    temp_data = {}
+    for measure_key, attr_key in (("betweenness", "node_betweenness"), ("betweenness_beta", "node_betweenness_beta")):
+        for d in resolved:
+            temp_data[config.prep_gdf_key(measure_key, d)] = getattr(result, attr_key)[d]
+    return _write(nodes_gdf, temp_data, result.node_keys_py)
+
+
 # ---- closeness-only / betweenness-only conveniences (networks.py:763-888)
 def closeness_shortest(network_structure, nodes_gdf, **kw):
     return node_centrality_shortest(network_structure, nodes_gdf, compute_closeness=True, compute_betweenness=False, **kw)

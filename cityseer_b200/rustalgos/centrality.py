@@ -85,3 +85,37 @@ class CentralitySegmentResult(_ResultBase):
     segment_harmonic = _getter(1)
     segment_beta = _getter(2)
     segment_betweenness = _getter(3)
+
+
+class BetweennessShortestResult(_ResultBase):
+    """centrality.rs:93-150 — result of ``betweenness_od_shortest``."""
+
+    node_betweenness = _getter(5)
+    node_betweenness_beta = _getter(6)
+
+
+class OdMatrix:
+    """Sparse origin-destination trip weights (centrality.rs:54-91): ``{origin: {destination: weight}}`` built from
+    parallel arrays; a repeated (origin, destination) pair keeps the last weight, like the reference's HashMap insert."""
+
+    def __init__(self, origins, destinations, weights):
+        origins, destinations, weights = list(origins), list(destinations), list(weights)
+        if len(origins) != len(destinations) or len(origins) != len(weights):
+            raise ValueError(
+                f"origins ({len(origins)}), destinations ({len(destinations)}), and weights ({len(weights)}) "
+                "must have equal length"
+            )
+        self.map: dict[int, dict[int, float]] = {}
+        for o, d, w in zip(origins, destinations, weights):
+            o, d = int(o), int(d)
+            if o < 0 or d < 0:
+                raise OverflowError("can't convert negative int to unsigned")
+            self.map.setdefault(o, {})[d] = float(np.float32(w))
+
+    def len(self) -> int:
+        """Number of non-zero OD pairs."""
+        return sum(len(d) for d in self.map.values())
+
+    def n_origins(self) -> int:
+        """Number of unique origin nodes."""
+        return len(self.map)

@@ -755,6 +755,49 @@ class NetworkStructure:
             res.reachability_totals = [int(x) for x in stats["reach_totals"]] if compute_closeness else [0] * len(d)
         return res
 
+    def betweenness_od_shortest(
+        self,
+        od_matrix,
+        distances=None,
+        betas=None,
+        minutes=None,
+        min_threshold_wt=None,
+        speed_m_s=None,
+        tolerance=None,
+        pbar_disabled=None,
+    ) -> "_centrality.BetweennessShortestResult":
+        """centrality.rs:2419-2540 — OD-weighted betweenness: one capped search per live origin with outbound trips, the
+        dependency pass seeded at its destinations only (weight w, beta seed ``w * exp(-beta * cost)``)."""
+        from . import pair_distances_betas_time, WALKING_SPEED
+
+        if not isinstance(od_matrix, _centrality.OdMatrix):
+            raise TypeError("argument 'od_matrix': expected OdMatrix")
+        speed = float(WALKING_SPEED if speed_m_s is None else np.float32(speed_m_s))
+        d, b, s = pair_distances_betas_time(speed, distances, betas, minutes, min_threshold_wt)
+        tol = _centrality.validate_tolerance(tolerance)
+        f = self.frozen()
+        live = f.live.astype(bool) & f.node_exists.astype(bool)
+        sources, od_off, od_dst, od_w = [], [0], [], []
+        for src in f.node_indices.tolist():  # the reference iterates node_indices and skips the rest (:2470-2481)
+            dests = od_matrix.map.get(src)
+            if not live[src] or not dests:
+                continue
+            for dest, w in dests.items():
+                if dest >= f.node_bound:
+                    raise ValueError(f"OD destination {dest} is out of range for node_bound {f.node_bound}")
+                od_dst.append(dest)
+                od_w.append(w)
+            sources.append(src)
+            od_off.append(len(od_dst))
+        self.progress_init()
+        dev = self.device_graph()
+        out, stats = dev.betweenness_od_shortest(
+            d, b, s, speed, tol, np.asarray(sources, np.uint32), np.asarray(od_off, np.uint64),
+            np.asarray(od_dst, np.uint32), np.asarray(od_w, np.float32),
+            None if pbar_disabled else self._progress, len(f.node_indices),
+        )  # fmt: skip
+        return _centrality.BetweennessShortestResult(d, self._node_keys_shared(), f.node_indices, out, stats)
+
     def centrality_simplest(
         self,
         distances=None,

@@ -123,6 +123,17 @@ int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distances, const f
                           float speed_m_s, int compute_closeness, int compute_betweenness, uint64_t n_sources,
                           const uint32_t* sources, double* out, int out_on_device, int accumulate, cs_stats* stats);
 
+/* Replaces NetworkStructure.betweenness_od_shortest (centrality.rs:2419-2540): the dependency pass of centrality_shortest
+ * seeded only at the OD destinations of every origin (weight w, beta seed w * exp(-beta * cost)); credits are not scaled
+ * by a source weight.  `sources` are the live origins with outbound trips; the destinations / weights of sources[k] are
+ * od_dst / od_w [od_off[k], od_off[k + 1]) (destinations unique per origin, as the reference's HashMap makes them).
+ * `out` uses the [7][D][node_bound] layout of cs_centrality_shortest; only rows 5 (betweenness) and 6 (betweenness_beta)
+ * are populated. */
+int cs_betweenness_od_shortest(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
+                               float speed_m_s, float tolerance, uint64_t n_sources, const uint32_t* sources,
+                               const uint64_t* od_off, const uint32_t* od_dst, const float* od_w, double* out,
+                               int out_on_device, cs_stats* stats);
+
 /* Replaces NetworkStructure.progress() (graph.rs:413): sources finished by the call in flight on this graph
  * (readable from another host thread while a compute call blocks). */
 uint64_t cs_progress(cs_graph* g);

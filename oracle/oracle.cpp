@@ -706,6 +706,44 @@ void orc_graph_destroy(orc_graph* h) { delete h; }
 
 // counters_out[7]: sources, settled, edge_iters, sum_ri, sum_ci, key_ties, multi_pred
 // out: [7][D][node_bound] = density, farness, cycles, harmonic, beta, betweenness, betweenness_beta
+// betweenness_od_shortest (centrality.rs:2419-2540): the Brandes pass of centrality_shortest with seeds only at the OD
+// destinations of each origin (weight w, beta seed w * exp(-beta * cost)), credits not scaled by any source weight.
+// od_off[k] .. od_off[k + 1] index the destinations / weights of sources[k]; out is [2][D][node_bound].
+int orc_betweenness_od(const orc_graph* h, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
+                       float speed, float tol, uint64_t n_sources, const uint32_t* sources, const uint64_t* od_off,
+                       const uint32_t* od_dst, const float* od_w, double* out, int n_threads) {
+    const Graph& g = h->g;
+    size_t nb = g.node_bound;
+    uint32_t max_sec = *std::max_element(seconds, seconds + D);
+    auto M = [&](int m, int i, size_t node) -> double* { return out + ((size_t)m * D + i) * nb + node; };
+    par_for(n_sources, n_threads, [&](uint64_t k) {
+        uint32_t src = sources[k];
+        Traversal t;
+        brandes_shortest(g, src, max_sec, speed, tol, t, nullptr);
+        std::vector<uint32_t> sorted = sorted_states(t);
+        std::vector<double> seed(t.state.size()), seedb(t.state.size());
+        for (int i = 0; i < D; ++i) {
+            float thr = (float)distances[i];
+            double beta = (double)betas[i];
+            std::fill(seed.begin(), seed.end(), 0.0);
+            std::fill(seedb.begin(), seedb.end(), 0.0);
+            for (uint64_t j = od_off[k]; j < od_off[k + 1]; ++j) {
+                uint32_t dest = od_dst[j];
+                if (t.best_route_cost[dest] > thr) continue;
+                seed[dest] += (double)od_w[j];
+                seedb[dest] += (double)od_w[j] * std::exp(-beta * (double)t.best_route_cost[dest]);
+            }
+            backprop(
+                t, sorted, src, seed, seedb, [&](const BState& s) { return s.route_cost <= thr; },
+                [&](uint32_t node, double credit, double creditb) {
+                    if (credit > 0.0) atomic_add(M(0, i, node), credit);
+                    if (creditb > 0.0) atomic_add(M(1, i, node), creditb);
+                });
+        }
+    });
+    return 0;
+}
+
 int orc_centrality_shortest(const orc_graph* h, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
                             float speed, float tol, int closeness, int betweenness, uint64_t n_sources,
                             const uint32_t* sources, const float* source_wt, const uint8_t* eligible, double* out,

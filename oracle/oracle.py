@@ -117,6 +117,23 @@ class OracleGraph:
         assert rc == 0
         return out, dict(zip(COUNTER_NAMES, cnt.tolist()), reach_totals=reach.tolist())
 
+    def betweenness_od(self, d, b, s, speed, sources, od_off, od_dst, od_w, tol=1e-4, n_threads=1):
+        """centrality.rs:2419-2540 — returns float64 [2][D][node_bound] (betweenness, betweenness_beta)."""
+        D = len(d)
+        out = np.zeros((2, D, self.nb), np.float64)
+        da, ba, sa = (np.ascontiguousarray(d, np.uint32), np.ascontiguousarray(b, np.float32), np.ascontiguousarray(s, np.uint32))
+        sources = np.ascontiguousarray(sources, np.uint32)
+        od_off = np.ascontiguousarray(od_off, np.uint64)
+        od_dst = np.ascontiguousarray(od_dst, np.uint32)
+        od_w = np.ascontiguousarray(od_w, np.float32)
+        L = lib()
+        L.orc_betweenness_od.restype = C.c_int
+        rc = L.orc_betweenness_od(self._h, C.c_int(D), _p(da, _u32p), _p(ba, _f32p), _p(sa, _u32p), C.c_float(speed),
+                                  C.c_float(tol), C.c_uint64(len(sources)), _p(sources, _u32p), _p(od_off, _u64p),
+                                  _p(od_dst, _u32p), _p(od_w, _f32p), _p(out, _f64p), C.c_int(n_threads))  # fmt: skip
+        assert rc == 0
+        return out
+
     def centrality_simplest(self, d, s, speed, tol=1e-4, unit=180.0, offset=1.0, closeness=True, betweenness=True,
                             sources=None, wt=None, eligible=None, n_threads=1):  # fmt: skip
         D = len(d)
