@@ -216,7 +216,7 @@ class DeviceGraph:
             raise ValueError(_err(self._lib))
 
     def set_option(self, name: str, value: float) -> None:
-        """Named tunables (``kernel``, ``page_bits``, ``delta_factor``); see include/cityseer_b200.h."""
+        """Named tunables (``kernel``, ``delta_factor``); see include/cityseer_b200.h."""
         if self._lib.cs_graph_set_option(self._h, name.encode(), float(value)):
             raise ValueError(_err(self._lib))
 

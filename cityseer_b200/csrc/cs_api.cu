@@ -10,10 +10,7 @@
 #include <string>
 #include <vector>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include "cs_shortest.cuh"
-#include "cs_shortest2.cuh"
 #include "cs_shortest3.cuh"
 #include "cs_segment.cuh"
 #include "cs_simplest.cuh"
@@ -83,31 +80,6 @@ struct cs_graph {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long* h_progress = nullptr;  // pinned
     std::mutex side_mu;
-    // shared-memory kernel (cs_shortest2.cuh): renumbered graph, new-id source plan, capacity plan
-    bool v2_ok = false;
-    uint32_t *d_orig_of_new = nullptr, *d_new_of_orig = nullptr;
-    uint4* d_node2 = nullptr;
-    CsEdge *d_in2 = nullptr, *d_out2 = nullptr;
-    float *d_in2_num = nullptr, *d_out2_num = nullptr;
-    float cached_speed2 = -1.f;
-    uint32_t *d_sources2 = nullptr, *d_sort_keys = nullptr, *d_sort_vals = nullptr, *d_sort_vals2 = nullptr;
-    uint32_t *d_fallback = nullptr, *d_fb_sources = nullptr, *d_fb2_sources = nullptr, *d_probe = nullptr;
-    float *d_src_wt2 = nullptr, *d_fb_wt = nullptr, *d_fb2_wt = nullptr;
-    uint8_t* d_eligible2 = nullptr;
-    void* d_cub_tmp = nullptr;
-    size_t cub_tmp_bytes = 0;
-    uint64_t sources2_cap = 0, n_sources2 = 0;
-    bool sources2_valid = false;
-    uint8_t* d_scratch2 = nullptr;
-    size_t scratch2_bytes = 0;
-    struct {
-        bool valid = false, use = false;
-        float max_seconds = 0.f, speed = 0.f;
-        int D = 0, ctas_per_sm = 0, T = 256;
-        uint32_t pb = 0, probe_R = 0, probe_pages = 0;
-        uint64_t n_sources = 0;
-        CsV2Smem sm{}, sm_big{};
-    } plan;
     // chain-contracted kernel (cs_shortest3.cuh)
     bool v3_ok = false;
     uint32_t v3_J = 0, v3_I = 0;
@@ -125,15 +97,8 @@ struct cs_graph {
     size_t od_off_cap = 0, od_pairs_cap = 0;
     int last_kernel = 1;
     int opt_kernel = 0;  // 0 auto (chain-contracted kernel when the graph qualifies, else the global-arena kernel),
-                         // 1 global-arena kernel, 2 shared-memory kernel, 3 chain-contracted kernel (required)
-    uint32_t opt_pb = 3;
+                         // 1 global-arena kernel, 3 chain-contracted kernel (required)
     float opt_delta_factor = 12.0f;
-    float opt_headroom = 1.1f;  // capacity of the primary shared-memory layout relative to the probed maxima
-    int opt_threads = 0;        // 0 = by reach, else 128 or 256 threads per CTA
-    uint64_t last_fallback = 0;
-    bool last_v2 = false;
-    uint32_t opt_reach_limit = 0, opt_reach_limit2 = 0;  // test hooks: cap the reached-node capacity of the primary /
-                                                         // largest shared-memory layout (forces the fallback passes)
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -218,11 +183,6 @@ static int upload(T** dptr, const std::vector<T>& h) {
     return 0;
 }
 
-static int build_v2_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, const double* xs, const double* ys,
-                          const std::vector<uint32_t>& in_off, const std::vector<uint32_t>& out_off,
-                          const std::vector<CsEdge>& in_rec, const std::vector<CsEdge>& out_rec,
-                          const std::vector<float>& in_num, const std::vector<float>& out_num,
-                          const std::vector<float>& weight, const std::vector<uint8_t>& live, uint32_t max_deg);
 static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, const double* xs, const double* ys,
                           const std::vector<uint32_t>& in_off, const std::vector<uint32_t>& out_off,
                           const std::vector<CsEdge>& in_rec, const std::vector<CsEdge>& out_rec,
@@ -442,7 +402,6 @@ extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_ex
         rc |= upload(&g->d_ang_rec, ang_rec);
         rc |= upload(&g->d_ang_num, ang_num);
     }
-    if (!rc) rc = build_v2_graph(g, n, node_exists, xs, ys, in_off, out_off, in_rec, out_rec, in_num, out_num, w, lv, max_deg);
     if (!rc) rc = build_v3_graph(g, n, node_exists, xs, ys, in_off, out_off, in_rec, out_rec, in_num, out_num, w);
     if (rc) {
         delete g;
@@ -468,15 +427,10 @@ extern "C" void cs_graph_destroy(cs_graph* g) {
     for (void* p : {(void*)g->d_in_off, (void*)g->d_out_off, (void*)g->d_in_rec, (void*)g->d_out_rec, (void*)g->d_ang_rec,
                     (void*)g->d_in_num, (void*)g->d_out_num, (void*)g->d_ang_num, (void*)g->d_in_imp, (void*)g->d_weight,
                     (void*)g->d_live, (void*)g->d_sources, (void*)g->d_src_wt, (void*)g->d_eligible, (void*)g->d_counters,
-                    (void*)g->d_error, (void*)g->d_out, (void*)g->d_arena, (void*)g->d_acc, (void*)g->d_orig_of_new,
-                    (void*)g->d_new_of_orig, (void*)g->d_node2, (void*)g->d_in2, (void*)g->d_out2, (void*)g->d_in2_num,
-                    (void*)g->d_out2_num, (void*)g->d_sources2, (void*)g->d_sort_keys, (void*)g->d_sort_vals,
-                    (void*)g->d_sort_vals2, (void*)g->d_fallback, (void*)g->d_fb_sources, (void*)g->d_probe,
-                    (void*)g->d_src_wt2, (void*)g->d_fb_wt, (void*)g->d_eligible2, g->d_cub_tmp, (void*)g->d_scratch2,
-                    (void*)g->d_fb2_sources, (void*)g->d_fb2_wt, (void*)g->d3_jinfo, (void*)g->d3_links, (void*)g->d3_ctab,
-                    (void*)g->d3_cnum, (void*)g->d3_csec, (void*)g->d3_weight, (void*)g->d3_int_chain,
-                    (void*)g->d3_orig_of_new, (void*)g->d3_new_of_orig, (void*)g->d3_eligible, (void*)g->d_od_off,
-                    (void*)g->d_od_dst, (void*)g->d_od_w})
+                    (void*)g->d_error, (void*)g->d_out, (void*)g->d_arena, (void*)g->d_acc, (void*)g->d3_jinfo,
+                    (void*)g->d3_links, (void*)g->d3_ctab, (void*)g->d3_cnum, (void*)g->d3_csec, (void*)g->d3_weight,
+                    (void*)g->d3_int_chain, (void*)g->d3_orig_of_new, (void*)g->d3_new_of_orig, (void*)g->d3_eligible,
+                    (void*)g->d_od_off, (void*)g->d_od_dst, (void*)g->d_od_w})
         if (p) cudaFree(p);
     if (g->h_progress) cudaFreeHost(g->h_progress);
     for (auto& e : g->ev)
@@ -499,28 +453,14 @@ extern "C" int cs_graph_set_option(cs_graph* g, const char* name, double value) 
     if (!g || !name) return cs_fail("null graph or option name");
     const std::string k(name);
     if (k == "kernel") {
-        if (value != 0 && value != 1 && value != 2 && value != 3) return cs_fail("option kernel must be 0 (auto), 1, 2 or 3");
+        if (value != 0 && value != 1 && value != 3) return cs_fail("option kernel must be 0 (auto), 1 (arena) or 3 (chain-contracted)");
         g->opt_kernel = (int)value;
-    } else if (k == "page_bits") {
-        if (value < 2 || value > 6) return cs_fail("option page_bits must be in [2, 6]");
-        g->opt_pb = (uint32_t)value;
-    } else if (k == "smem_reach_limit") {
-        g->opt_reach_limit = (uint32_t)value;
-    } else if (k == "smem_reach_limit2") {
-        g->opt_reach_limit2 = (uint32_t)value;
-    } else if (k == "headroom") {
-        if (!(value >= 1.0)) return cs_fail("option headroom must be >= 1");
-        g->opt_headroom = (float)value;
-    } else if (k == "threads") {
-        if (value != 0 && value != 128 && value != 256 && value != 512) return cs_fail("option threads must be 0, 128, 256 or 512");
-        g->opt_threads = (int)value;
     } else if (k == "delta_factor") {
         if (!(value > 0)) return cs_fail("option delta_factor must be positive");
         g->opt_delta_factor = (float)value;
     } else {
         return cs_fail("unknown option %s", name);
     }
-    g->plan.valid = false;
     return 0;
 }
 
@@ -707,7 +647,6 @@ static int stage_sources(cs_graph* g, uint64_t n_sources, const uint32_t* source
     }
     for (uint64_t i = 0; i < n_sources; ++i)
         if (sources[i] >= g->n) return cs_fail("node index %u does not exist in the graph", sources[i]);
-    g->sources2_valid = false;
     if (n_sources) {
         CS_CUDA(cudaMemcpyAsync(g->d_sources, sources, n_sources * 4, cudaMemcpyHostToDevice, g->stream));
         if (source_wt)
@@ -769,11 +708,7 @@ static int finish_call(cs_graph* g, double* out, int out_on_device, size_t elems
         stats->relaxations = h[CS_C_RELAX];
         for (int i = 0; i < CS_MAX_THRESHOLDS; ++i) stats->reach_totals[i] = h[CS_C_REACH0 + i];
         for (int i = 0; i < 8; ++i) stats->phase_cycles[i] = h[CS_C_PHASE0 + i];
-        stats->fallback_sources = g->last_v2 ? g->last_fallback : 0;
-        stats->smem_bytes = g->last_v2 ? g->plan.sm.total : 0;
-        stats->ctas_per_sm = g->last_v2 ? (uint32_t)g->plan.ctas_per_sm : 0;
-        stats->reach_capacity = g->last_v2 ? g->plan.sm.rcap : 0;
-        stats->slot_capacity = g->last_v2 ? g->plan.sm.S : 0;
+        stats->reach_capacity = g->lay.rcap;
         stats->kernel_used = (uint32_t)g->last_kernel;
         cudaEventElapsedTime(&stats->kernel_ms, g->ev[1], g->ev[2]);
         cudaEventElapsedTime(&stats->total_ms, g->ev[0], g->ev[3]);
@@ -818,7 +753,6 @@ static float default_delta(const cs_graph* g, float speed) {
     return std::max(1e-3f, g->opt_delta_factor * g->mean_edge_len / speed);
 }
 
-#include "cs_api_v2.inl"
 #include "cs_api_v3.inl"
 
 template <int DT>
@@ -872,57 +806,6 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
     }
     uint32_t max_sec = 0;
     for (int i = 0; i < D; ++i) max_sec = std::max(max_sec, seconds[i]);
-
-    // ---- shared-memory kernel (cs_shortest2.cuh) when the graph and the call fit it
-    bool use_v2 = false;
-    CsShortest2Params q{};
-    if (g->opt_kernel == 2 && g->v2_ok && D <= 8 && n_sources > 0) {  // auto = the arena kernel: measured faster (profiles/r01d)
-        if (stage_sources_v2(g, n_sources, &launches)) return 1;
-        if (g->cached_speed2 != speed && g->E) {
-            const int blocks = (int)((g->E + 255) / 256);
-            cs_k_prep_seconds<<<blocks, 256, 0, g->stream>>>(g->d_in2, g->d_in2_num, g->E, speed);
-            cs_k_prep_seconds<<<blocks, 256, 0, g->stream>>>(g->d_out2, g->d_out2_num, g->E, speed);
-            launches += 2;
-            g->cached_speed2 = speed;
-        }
-        q.g.n = g->n;
-        q.g.node2 = g->d_node2;
-        q.g.in2 = g->d_in2;
-        q.g.out2 = g->d_out2;
-        q.g.orig_of_new = g->d_orig_of_new;
-        q.D = D;
-        q.closeness = closeness;
-        q.betweenness = betweenness;
-        q.phase2 = tol > CS_TIE_EPS ? 1 : 0;
-        for (int i = 0; i < D; ++i) {
-            q.dist_f[i] = (float)distances[i];
-            q.beta_f[i] = betas[i];
-            q.beta_d[i] = (double)betas[i];
-        }
-        q.max_seconds = (float)max_sec;
-        q.speed = speed;
-        q.tol = tol;
-        q.sources = g->d_sources2;
-        q.src_wt = g->d_src_wt2;
-        q.n_sources = n_sources;
-        q.eligible = g->d_eligible2;
-        q.acc_c = g->d_acc;
-        q.acc_b = g->d_acc + (size_t)g->n * cw;
-        q.cw = cw;
-        q.bw = bw;
-        q.counters = g->d_counters;
-        q.error = g->d_error;
-        q.fallback = g->d_fallback;
-        q.probe_max = g->d_probe;
-        q.delta = default_delta(g, speed);
-        q.dump_agg = dump_agg;
-        q.dump_sigma = dump_sigma;
-        q.dump_npred = dump_npred;
-        if (v2_plan(g, q, n_sources, &launches)) return 1;
-        use_v2 = g->plan.use;
-    }
-    if (g->opt_kernel == 2 && !use_v2)
-        return cs_fail("the shared-memory kernel cannot serve this call (degree > %d, D > 8, or no layout fits)", CS2_MAX_DEG);
 
     CS_CUDA(cudaMemsetAsync(g->d_counters, 0, CS_NCOUNTERS * sizeof(unsigned long long), g->stream));
     CS_CUDA(cudaMemsetAsync(g->d_acc, 0, acc_elems * sizeof(double), g->stream));
@@ -1008,7 +891,11 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
 
     // ---- chain-contracted kernel (cs_shortest3.cuh): junction-level search, chains walked in place
     const bool dumping = dump_agg || dump_sigma || dump_npred || od_off;  // served by the arena kernel
-    bool use_v3 = !use_v2 && !dumping && g->v3_ok && n_sources > 0 && (g->opt_kernel == 3 || g->opt_kernel == 0);
+    // auto: the chain-contracted kernel pays off when most nodes are chain interiors (decomposed / OSM-like graphs:
+    // cfg #4 1.07 M vs 0.47 M sources/s); on a graph of junctions only the arena kernel is the faster one (cfg #2:
+    // 3.7 M vs 2.1 M sources/s)
+    bool use_v3 = !dumping && g->v3_ok && n_sources > 0 &&
+                  (g->opt_kernel == 3 || (g->opt_kernel == 0 && g->v3_I >= g->v3_J));
     if (g->opt_kernel == 3 && !use_v3 && !dumping && n_sources > 0)
         return cs_fail("the chain-contracted kernel cannot serve this graph (an edge without a mutual twin, or a junction "
                        "with more than %d links)", CS3_MAX_LINKS);
@@ -1084,82 +971,17 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
             launches += 1;
             CS_CUDA(cudaGetLastError());
             CS_CUDA(cudaEventRecord(g->ev[2], g->stream));
-            g->last_v2 = false;
             g->last_kernel = 3;
             return finish_call(g, out, out_on_device, elems, d_out, stats, launches);
         }
     }
-    g->last_v2 = use_v2;
-    g->last_fallback = 0;
-    if (use_v2) g->last_kernel = 2;
-    if (use_v2) {
-        q.sm = g->plan.sm;
-        q.probe = 0;
-        q.bin_scale = (float)q.sm.NB / (((float)max_sec + 1.0f) * ((float)max_sec + 1.0f));
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_sources, (uint64_t)g->sm_count * g->plan.ctas_per_sm);
-        const uint32_t grid_big = (uint32_t)g->sm_count;
-        size_t stride = 0, stride_big = 0;
-        if (v2_scratch(g, g->plan.sm_big, D, grid_big, &stride_big)) return 1;
-        if (v2_scratch(g, q.sm, D, grid, &stride)) return 1;
-        q.scratch = g->d_scratch2;
-        q.scratch_stride = stride;
-        g->workers = grid;
-        CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
-        CS_CUDA(v2_launch(q, g->plan.T, grid, g->stream, nullptr));
-        launches += 1;
-        // sources that did not fit the primary layout: once more at the largest layout, then the global-arena kernel
-        unsigned long long n_fb = 0;
-        CS_CUDA(cudaMemcpyAsync(&n_fb, g->d_counters + CS_C_FALLBACK, sizeof(n_fb), cudaMemcpyDeviceToHost, g->stream));
-        CS_CUDA(cudaStreamSynchronize(g->stream));
-        g->last_fallback = n_fb;
-        if (n_fb > 0 && g->plan.sm_big.total > q.sm.total) {
-            cs_k_gather_fallback_new<<<(int)((n_fb + 255) / 256), 256, 0, g->stream>>>(g->d_fallback, n_fb, g->d_sources2,
-                                                                                      g->d_src_wt2, g->d_fb_sources, g->d_fb_wt);
-            CS_CUDA(cudaMemsetAsync(g->d_counters + CS_C_NEXT, 0, sizeof(unsigned long long), g->stream));
-            CS_CUDA(cudaMemsetAsync(g->d_counters + CS_C_FALLBACK, 0, sizeof(unsigned long long), g->stream));
-            CsShortest2Params q2 = q;
-            q2.sm = g->plan.sm_big;
-            q2.bin_scale = (float)q2.sm.NB / (((float)max_sec + 1.0f) * ((float)max_sec + 1.0f));
-            q2.sources = g->d_fb_sources;
-            q2.src_wt = g->d_fb_wt;
-            q2.n_sources = n_fb;
-            q2.scratch_stride = stride_big;
-            CS_CUDA(v2_launch(q2, 256, (uint32_t)std::min<uint64_t>(n_fb, grid_big), g->stream, nullptr));
-            launches += 2;
-            CS_CUDA(cudaMemcpyAsync(&n_fb, g->d_counters + CS_C_FALLBACK, sizeof(n_fb), cudaMemcpyDeviceToHost, g->stream));
-            CS_CUDA(cudaStreamSynchronize(g->stream));
-            if (n_fb > 0)
-                cs_k_gather_fallback<<<(int)((n_fb + 255) / 256), 256, 0, g->stream>>>(
-                    g->d_fallback, n_fb, g->d_fb_sources, g->d_fb_wt, g->d_orig_of_new, g->d_fb2_sources, g->d_fb2_wt);
-        } else if (n_fb > 0) {
-            cs_k_gather_fallback<<<(int)((n_fb + 255) / 256), 256, 0, g->stream>>>(g->d_fallback, n_fb, g->d_sources2, g->d_src_wt2,
-                                                                                  g->d_orig_of_new, g->d_fb2_sources, g->d_fb2_wt);
-        }
-        cs_k_epilogue_shortest2<<<nblk, 256, 0, g->stream>>>(q.acc_c, q.acc_b, d_out, g->d_orig_of_new, g->n, D, cw, bw,
-                                                             closeness, betweenness, accumulate);
-        launches += 1;
-        CS_CUDA(cudaGetLastError());
-        if (n_fb > 0) {
-            CS_CUDA(cudaMemsetAsync(g->d_counters + CS_C_NEXT, 0, sizeof(unsigned long long), g->stream));
-            CS_CUDA(cudaMemsetAsync(g->d_acc, 0, acc_elems * sizeof(double), g->stream));
-            p.sources = g->d_fb2_sources;
-            p.src_wt = g->d_fb2_wt;
-            p.n_sources = n_fb;
-            if (launch_v1(n_fb)) return 1;
-            cs_k_epilogue_shortest<<<nblk, 256, 0, g->stream>>>(p.acc_c, p.acc_b, d_out, g->n, D, cw, bw, closeness, betweenness, 1);
-            launches += 2;
-            CS_CUDA(cudaGetLastError());
-        }
-        CS_CUDA(cudaEventRecord(g->ev[2], g->stream));
-    } else {
-        CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
-        if (launch_v1(n_sources)) return 1;
-        cs_k_epilogue_shortest<<<nblk, 256, 0, g->stream>>>(p.acc_c, p.acc_b, d_out, g->n, D, cw, bw, closeness, betweenness,
-                                                            accumulate);
-        launches += 1;
-        CS_CUDA(cudaGetLastError());
-        CS_CUDA(cudaEventRecord(g->ev[2], g->stream));
-    }
+    CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
+    if (launch_v1(n_sources)) return 1;
+    cs_k_epilogue_shortest<<<nblk, 256, 0, g->stream>>>(p.acc_c, p.acc_b, d_out, g->n, D, cw, bw, closeness, betweenness,
+                                                        accumulate);
+    launches += 1;
+    CS_CUDA(cudaGetLastError());
+    CS_CUDA(cudaEventRecord(g->ev[2], g->stream));
     return finish_call(g, out, out_on_device, elems, d_out, stats, launches);
 }
 

@@ -11,7 +11,7 @@ extern "C" int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distanc
     if (g->twin_missing)
         return cs_fail("Edge not found: segment_centrality needs the reverse twin of every directed edge (graph.rs:1291)");
     CS_CUDA(cudaSetDevice(g->device));
-    g->last_v2 = false;
+    g->last_kernel = 0;
     if (ensure_arena(g, 0, D)) return 1;
     uint32_t launches = 0;
     CS_CUDA(cudaEventRecord(g->ev[0], g->stream));
@@ -82,7 +82,7 @@ extern "C" int cs_centrality_simplest(cs_graph* g, int D, const uint32_t* distan
     if (!(speed_m_s > 0.f) || !std::isfinite(speed_m_s)) return cs_fail("speed_m_s must be finite and positive, got %f", speed_m_s);
     if (!(tolerance >= CS_TIE_EPS)) return cs_fail("Tolerance must be >= TIE_EPSILON to avoid float-comparison bugs");
     CS_CUDA(cudaSetDevice(g->device));
-    g->last_v2 = false;
+    g->last_kernel = 0;
     if (ensure_arena_angular(g, D)) return 1;
     uint32_t launches = 0;
     CS_CUDA(cudaEventRecord(g->ev[0], g->stream));

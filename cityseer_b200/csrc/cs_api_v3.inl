@@ -15,10 +15,28 @@
 // A graph qualifies when every non-loop directed edge has exactly one mutual twin (what io.network_structure_from_nx
 // produces) and no junction has more than CS3_MAX_LINKS links; otherwise the arena kernel serves the call.
 
-struct CsV3Host {
-    bool ok = false;
-    uint32_t J = 0, I = 0, C = 0;
-};
+// position of (x, y) along a Hilbert curve over a 2^bits x 2^bits grid
+static inline uint64_t hilbert_d(uint32_t x, uint32_t y, int bits) {
+    uint64_t d = 0;
+    for (uint32_t s = 1u << (bits - 1); s > 0; s >>= 1) {
+        const uint32_t rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+        d += (uint64_t)s * s * ((3u * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) {
+                x = s - 1 - x;
+                y = s - 1 - y;
+            }
+            std::swap(x, y);
+        }
+    }
+    return d;
+}
+
+// per-call flags by new id: dst[v] = src[orig_of_new[v]]
+__global__ void cs_k_permute_u8(const uint8_t* src, const uint32_t* orig_of_new, uint8_t* dst, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[orig_of_new[i]];
+}
 
 static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, const double* xs, const double* ys,
                           const std::vector<uint32_t>& in_off, const std::vector<uint32_t>& out_off,

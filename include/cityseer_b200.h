@@ -38,13 +38,14 @@ typedef struct cs_stats {
     uint32_t gpu_launches;    /* kernels launched by this call */
     uint32_t workers;         /* resident workers (warps or CTAs, one source each at a time) */
     uint64_t phase_cycles[8]; /* SM clock cycles summed over workers per kernel phase (search, order, predecessors,
-                                 closeness, dependencies, reset); [6], [7]: search iterations and bucket advances of the shared-memory kernel */
-    uint64_t fallback_sources; /* sources the shared-memory kernel handed to the global-arena kernel (capacity overflow) */
-    uint32_t smem_bytes;      /* shared-memory kernel: dynamic shared memory per CTA (0 = global-arena kernel ran) */
-    uint32_t ctas_per_sm;     /* shared-memory kernel: resident CTAs per SM */
-    uint32_t reach_capacity;  /* shared-memory kernel: reached nodes per source it can hold */
-    uint32_t slot_capacity;   /* shared-memory kernel: distance-map slots (pages x page size) */
-    uint32_t kernel_used;     /* centrality_shortest: 1 global-arena kernel, 2 shared-memory kernel, 3 chain-contracted kernel */
+                                 closeness, dependencies, reset); chain-contracted kernel: [6] dependency chunks,
+                                 [7] 32-link batches of the dependency pass */
+    uint64_t fallback_sources; /* reserved (0) */
+    uint32_t smem_bytes;      /* reserved (0) */
+    uint32_t ctas_per_sm;     /* reserved (0) */
+    uint32_t reach_capacity;  /* nodes (junctions, for the chain-contracted kernel) a source may reach: arena capacity */
+    uint32_t slot_capacity;   /* reserved (0) */
+    uint32_t kernel_used;     /* centrality_shortest: 1 global-arena kernel, 3 chain-contracted kernel */
     uint32_t reserved;
 } cs_stats;
 
@@ -79,9 +80,8 @@ void cs_graph_destroy(cs_graph* g);
 int cs_graph_configure(cs_graph* g, uint32_t reach_capacity, float delta_seconds, uint32_t workers);
 
 /* Named tunables of the search kernels: "kernel" (0 = choose per call: the chain-contracted kernel when the graph
- * qualifies, else the global-arena kernel; 1 = global-arena kernel only; 2 = require the shared-memory kernel;
- * 3 = require the chain-contracted kernel), "page_bits" (log2 nodes per shared-memory page, default 4), "delta_factor" (near/far bucket
- * width in mean edge traversal times, default 6). */
+ * qualifies, else the global-arena kernel; 1 = global-arena kernel only; 3 = require the chain-contracted kernel),
+ * "delta_factor" (near/far bucket width in mean edge traversal times, default 12). */
 int cs_graph_set_option(cs_graph* g, const char* name, double value);
 
 /* Run subsequent calls on a caller-owned CUDA stream (e.g. torch's current stream) so that a collective enqueued by the

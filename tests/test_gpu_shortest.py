@@ -14,10 +14,10 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # stated tolerance for floating-point metrics
 
 
-@pytest.fixture(autouse=True, params=[3, 2, 1], ids=["chain-kernel", "smem-kernel", "arena-kernel"])
+@pytest.fixture(autouse=True, params=[3, 1], ids=["chain-kernel", "arena-kernel"])
 def kernel_choice(request):
-    """Every test runs against all three search kernels: 3 = chain-contracted warp-per-source kernel and 2 = shared-memory
-    CTA-per-source kernel (both required, no silent fallback), 1 = global-arena warp-per-source kernel."""
+    """Every test runs against both search kernels: 3 = chain-contracted kernel (required, no silent fallback),
+    1 = global-arena kernel."""
     from cityseer_b200 import _native
 
     _native.DEFAULT_OPTIONS["kernel"] = float(request.param)
@@ -212,32 +212,3 @@ def test_linearity_property_full_size_graph():
     assert np.array_equal(a._out[0] + b._out[0], full._out[0])
     assert np.array_equal(a._out[2] + b._out[2], full._out[2])
     np.testing.assert_allclose(a._out[1] + b._out[1], full._out[1], rtol=1e-9)
-
-
-@pytest.mark.parametrize("limit2", [0, 512], ids=["second-pass", "second-pass+arena"])
-def test_smem_kernel_overflow_paths(oracle_mod, kernel_choice, limit2):
-    # sources whose reach exceeds the primary shared-memory layout are re-run at the largest layout, and what overflows
-    # that is re-run by the global-arena kernel; every path adds into the same result
-    if kernel_choice != 2:
-        pytest.skip("shared-memory kernel only")
-    ns, _ = synth.config("cfg2", 0.2)
-    dev = ns.device_graph()
-    dev.set_option("smem_reach_limit", 256)
-    if limit2:
-        dev.set_option("smem_reach_limit2", limit2)
-    res, ref, cnt = run_both(oracle_mod, ns, [500, 1000, 2000])
-    check(res._out, ref)
-    assert 0 < res.stats["fallback_sources"] < res.stats["sources"]
-    assert res.stats["settled"] == cnt["settled"] and res.stats["sum_ci"] == cnt["sum_ci"]
-    assert res.stats["sum_ri"] == cnt["sum_ri"] and res.stats["edge_iters"] == cnt["edge_iters"]
-
-
-@pytest.mark.parametrize("threads", [128, 256])
-def test_smem_kernel_thread_counts(oracle_mod, kernel_choice, threads):
-    if kernel_choice != 2:
-        pytest.skip("shared-memory kernel only")
-    ns, _ = synth.config("cfg4", 0.06)
-    ns.device_graph().set_option("threads", threads)
-    res, ref, cnt = run_both(oracle_mod, ns, [500, 1000, 2000])
-    check(res._out, ref)
-    assert res.stats["settled"] == cnt["settled"] and res.stats["sum_ci"] == cnt["sum_ci"]
