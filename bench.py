@@ -137,7 +137,7 @@ def run_reference(args):
         return
     ns, info = build_graph()
     threads = host_threads()
-    n_sample = args.cpu_sample or max(64, 16 * threads)
+    n_sample = args.cpu_sample or max(64, 64 * threads)  # ~4 s of CPU work per step on the GPU box's host
     for _ in range(args.warmup):
         cpu_sample(ns, max(threads, n_sample // 8), threads, seed=1)
     t0 = time.perf_counter()
@@ -287,7 +287,7 @@ def run_ours(args):
         cpu = None
         if ws == 1 and not args.no_cpu:
             threads = host_threads()
-            n_sample = args.cpu_sample or max(64, 16 * threads)
+            n_sample = args.cpu_sample or max(256, 160 * threads)  # bounded sample: ~10 s of CPU work
             r, g, dt = cpu_sample(ns, n_sample, threads)
             cpu = {"value": r, "unit": "sources/s", "cores": threads, "kind": "port", "gteps": g,
                    "sample": f"{n_sample} random sources (seed 7) of the same graph and thresholds, {dt:.1f} s"}  # fmt: skip

@@ -90,6 +90,9 @@ SIGNATURES = {
         [C.c_void_p, C.c_int, _u32p, _f32p, _u32p, C.c_float, C.c_float, C.c_uint64, _u32p, _u64p, _u32p, _f32p,
          C.c_void_p, C.c_int, C.POINTER(CsStats)],
     ),  # fmt: skip
+    "cs_dijkstra_tree_shortest": (
+        C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, _u32p, _u32p, C.POINTER(C.c_int64), _f32p],
+    ),
     "cs_progress": (C.c_uint64, [C.c_void_p]),
     "cs_shortest_search": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _f32p, _f64p, _u32p]),
 }
@@ -381,7 +384,21 @@ class DeviceGraph:
         return agg, sig, npred
 
     def dijkstra_tree(self, kind: int, src_idx: int, max_seconds: int, speed: float):
-        raise NotImplementedError(
-            "dijkstra_tree_* (single-source tree dumps) are the next row of the scope table (SURVEY.md §8f-3); "
-            "not built in this round"
-        )
+        """kind 0 = dijkstra_tree_shortest: (visited order, predecessor per node (-1 none), seconds per node)."""
+        if kind != 0:
+            raise NotImplementedError(
+                "dijkstra_tree_simplest / dijkstra_tree_segment (single-source dumps) are the next row of the scope table "
+                "(SURVEY.md §8f-3); dijkstra_tree_shortest is served by the device"
+            )
+        n = self.node_bound
+        nv = C.c_uint32(0)
+        order = np.zeros(max(n, 1), np.uint32)
+        pred = np.zeros(max(n, 1), np.int64)
+        agg = np.zeros(max(n, 1), np.float32)
+        with self._call_lock:
+            rc = self._lib.cs_dijkstra_tree_shortest(self._h, int(src_idx), int(max_seconds), float(speed), C.byref(nv),
+                                                     _ptr(order, _u32p), pred.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                     _ptr(agg, _f32p))  # fmt: skip
+            if rc:
+                raise ValueError(_err(self._lib))
+        return order[: nv.value], pred[:n], agg[:n]

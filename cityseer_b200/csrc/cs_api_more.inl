@@ -1,3 +1,80 @@
+// ------------------------------------------------------------------------------------------------ single-source tree
+// dijkstra_tree_shortest (centrality.rs:1141-1200, :1499-1508): the capped search of the segment kernel (distances by
+// the label-correcting search, exact settle order, single predecessor = the first strict improvement in pop order) run
+// for one source with the accumulation phases off, its per-node state downloaded.
+extern "C" int cs_dijkstra_tree_shortest(cs_graph* g, uint32_t src, uint32_t max_seconds, float speed_m_s,
+                                         uint32_t* n_visited, uint32_t* visited_order, int64_t* pred, float* agg_seconds) {
+    if (!g) return cs_fail("null graph");
+    if (!n_visited || !visited_order || !pred || !agg_seconds) return cs_fail("null output");
+    if (src >= g->n) return cs_fail("src_idx %u out of range for network with node_bound %u", src, g->n);
+    if (!(speed_m_s > 0.f) || !std::isfinite(speed_m_s)) return cs_fail("speed_m_s must be finite and positive, got %f", speed_m_s);
+    CS_CUDA(cudaSetDevice(g->device));
+    g->last_kernel = 0;
+    if (ensure_arena(g, 0, 1)) return 1;
+    uint32_t launches = 0;
+    if (stage_sources(g, 1, &src, nullptr, nullptr)) return 1;
+    if (prep_seconds(g, speed_m_s, false, &launches)) return 1;
+    CS_CUDA(cudaMemsetAsync(g->d_counters, 0, CS_NCOUNTERS * sizeof(unsigned long long), g->stream));
+    CS_CUDA(cudaMemsetAsync(g->d_error, 0, sizeof(int), g->stream));
+    const size_t n = g->n;
+    uint32_t *d_order = nullptr, *d_pred = nullptr, *d_count = nullptr;
+    float* d_agg = nullptr;
+    CS_CUDA(cudaMalloc(&d_order, n * 4));
+    CS_CUDA(cudaMalloc(&d_pred, n * 4));
+    CS_CUDA(cudaMalloc(&d_agg, n * 4));
+    CS_CUDA(cudaMalloc(&d_count, 4));
+    CS_CUDA(cudaMemsetAsync(d_pred, 0xff, n * 4, g->stream));
+    CS_CUDA(cudaMemsetAsync(d_count, 0, 4, g->stream));
+    {
+        std::vector<float> inf(n, INFINITY);
+        CS_CUDA(cudaMemcpyAsync(d_agg, inf.data(), n * 4, cudaMemcpyHostToDevice, g->stream));
+        CS_CUDA(cudaStreamSynchronize(g->stream));
+    }
+    CsSegmentParams p{};
+    p.g = graph_dev(g);
+    p.D = 1;
+    p.closeness = 0;
+    p.betweenness = 0;
+    p.dist_f[0] = 0.f;
+    p.beta_f[0] = 0.f;
+    p.max_seconds = (float)max_seconds;
+    p.speed = speed_m_s;
+    p.sources = g->d_sources;
+    p.n_sources = 1;
+    p.out = nullptr;
+    p.counters = g->d_counters;
+    p.error = g->d_error;
+    p.arena = g->d_arena;
+    p.lay = g->lay;
+    p.delta = default_delta(g, speed_m_s);
+    p.bin_scale = (float)CS_NBINS / (((float)max_seconds + 1.0f) * ((float)max_seconds + 1.0f));
+    p.dump_order = d_order;
+    p.dump_pred = d_pred;
+    p.dump_agg = d_agg;
+    p.dump_count = d_count;
+    cs_k_segment<1><<<1, CS_WARPS_PER_CTA * 32, 0, g->stream>>>(p);
+    int rc = 0;
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(g->stream) != cudaSuccess) rc = cs_fail("CUDA error in the tree search");
+    int herr = 0;
+    if (!rc) {
+        cudaMemcpy(&herr, g->d_error, sizeof(int), cudaMemcpyDeviceToHost);
+        if (herr) rc = cs_fail("search arena overflow: the source reached more than %u nodes; raise reach_capacity via cs_graph_configure", g->lay.rcap);
+    }
+    if (!rc) {
+        std::vector<uint32_t> hp(n);
+        cudaMemcpy(n_visited, d_count, 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(visited_order, d_order, (size_t)*n_visited * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hp.data(), d_pred, n * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(agg_seconds, d_agg, n * 4, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < n; ++i) pred[i] = hp[i] == 0xffffffffu ? -1 : (int64_t)hp[i];
+    }
+    cudaFree(d_order);
+    cudaFree(d_pred);
+    cudaFree(d_agg);
+    cudaFree(d_count);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------------ segment
 extern "C" int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
                                      float speed_m_s, int compute_closeness, int compute_betweenness, uint64_t n_sources,

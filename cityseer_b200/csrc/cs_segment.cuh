@@ -24,6 +24,12 @@ struct CsSegmentParams {
     uint8_t* arena;
     CsArenaLayout lay;
     float delta, bin_scale;
+    // single-source tree dump (dijkstra_tree_shortest, centrality.rs:1141-1200): settle order, predecessor and
+    // seconds per node; NULL for centrality runs
+    uint32_t* dump_order;  // [n] nodes in settle order
+    uint32_t* dump_pred;   // [n] predecessor node, 0xffffffff = none
+    float* dump_agg;       // [n] seconds (prefilled with inf by the caller)
+    uint32_t* dump_count;  // [1] number of settled nodes
 };
 
 // one side of a visited edge: integrals of 1, 1/x, exp(-beta x) from `lo` towards `hi_raw`, clipped at the threshold
@@ -116,6 +122,12 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_seg
                 }
                 pred_rank = best_key;
                 cs_st(&A.predmask[r], pred_rank == CS_NOSLOT ? 0u : (1u << best_j));
+                if (p.dump_order) {
+                    p.dump_order[r] = v;
+                    p.dump_agg[v] = av;
+                    p.dump_pred[v] = pred_rank == CS_NOSLOT ? 0xffffffffu : cs_ld(&A.s_node[pred_rank]);
+                    if (r == 0) *p.dump_count = R;
+                }
                 // closeness over the edges visited from v: incoming (m->v) with m not settled before v, or a self-loop
                 if (p.closeness) {
                     const float dn = __fmul_rn(av, p.speed);

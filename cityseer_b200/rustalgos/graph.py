@@ -901,7 +901,18 @@ class NetworkStructure:
     def dijkstra_tree_shortest(self, src_idx: int, max_seconds: int, speed_m_s: float):
         """centrality.rs:1499-1508 — device search; returns ``(visited_nodes, tree_map)``."""
         self._validate_dijkstra_inputs(src_idx, float(speed_m_s))
-        return self.device_graph().dijkstra_tree(0, src_idx, int(max_seconds), float(np.float32(speed_m_s)))
+        speed = np.float32(speed_m_s)
+        order, pred, agg = self.device_graph().dijkstra_tree(0, src_idx, int(max_seconds), float(speed))
+        tree_map = [NodeVisit() for _ in range(len(pred))]
+        short = agg * speed  # f32 product, as total_seconds * speed_m_s (:1188)
+        for i in order.tolist():
+            t = tree_map[i]
+            t.visited = True
+            t.discovered = True
+            t.pred = None if pred[i] < 0 else int(pred[i])
+            t.agg_seconds = float(agg[i])
+            t.short_dist = float(short[i])
+        return order.tolist(), tree_map
 
     def dijkstra_tree_simplest(self, src_idx: int, max_seconds: int, speed_m_s: float):
         """centrality.rs:1510-1521"""

@@ -134,6 +134,13 @@ int cs_betweenness_od_shortest(cs_graph* g, int D, const uint32_t* distances, co
                                const uint64_t* od_off, const uint32_t* od_dst, const float* od_w, double* out,
                                int out_on_device, cs_stats* stats);
 
+/* Replaces NetworkStructure.dijkstra_tree_shortest (centrality.rs:1141-1200, :1499-1508): one capped search from
+ * `src`; `visited_order[0 .. *n_visited)` are the settled nodes in pop order, `pred[i]` the predecessor of node i
+ * (-1 = none) and `agg_seconds[i]` its travel time (inf = not reached); pred / agg_seconds are sized node_bound,
+ * visited_order at least node_bound. */
+int cs_dijkstra_tree_shortest(cs_graph* g, uint32_t src, uint32_t max_seconds, float speed_m_s, uint32_t* n_visited,
+                              uint32_t* visited_order, int64_t* pred, float* agg_seconds);
+
 /* Replaces NetworkStructure.progress() (graph.rs:413): sources finished by the call in flight on this graph
  * (readable from another host thread while a compute call blocks). */
 uint64_t cs_progress(cs_graph* g);
