@@ -251,15 +251,12 @@ def run_ours(args):
 
     # ---- end-to-end through the public API: host plan in, host result out, every step
     dev.set_stream(None)
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 5))
     h2d = batch * 8 + N
     d2h = 7 * D * N * 8
-    torch.cuda.synchronize()
-    if ws > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        src = block(args.warmup + args.steps + k)
+
+    def e2e_step(k: int):
+        src = block(k)
         if ws == 1:
             ns.centrality_shortest(distances=DISTANCES, source_indices=src, sample_probability=1.0, pbar_disabled=True)
         else:
@@ -268,6 +265,14 @@ def run_ours(args):
                                     len(src), out_device_ptr=part.data_ptr())  # fmt: skip
             dist.all_reduce(part)
             part.cpu()
+
+    e2e_step(args.warmup + args.steps)  # untimed warm-up of this path (page-locked result buffer, key list)
+    torch.cuda.synchronize()
+    if ws > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(args.warmup + args.steps + 1 + k)
     torch.cuda.synchronize()
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
     if ws > 1:

@@ -786,6 +786,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
         // ------------------------------------------------------------------ P4: closeness scatter to targets
         unsigned long long n_ri = 0, n_ci = 0;
         uint32_t n_chunks = 0, n_batches = 0;
+        float cycles_wt = 0.f;
         if (p.closeness) {
             if (lane < (uint32_t)D) {
                 long long ncount = 0, ecount = 0;
@@ -797,7 +798,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 atomicAdd(&p.counters[CS_C_REACH0 + lane], (unsigned long long)(ncount > 0 ? ncount - 1 : 0));
             }
             __syncwarp();
-            const float cycles_wt = __fdiv_rn(wt, __ldg(&g.weight[S.id]));  // centrality.rs:1730
+            cycles_wt = __fdiv_rn(wt, __ldg(&g.weight[S.id]));  // centrality.rs:1730
             for (uint32_t b0 = 0; b0 < R; b0 += 32) {
                 const uint32_t r = b0 + lane;
                 uint32_t v = 0, off = 0, deg = 0;
@@ -820,8 +821,9 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 l_cost[lane] = (r < R && r != 0) ? __fmul_rn(av, p.speed) : __uint_as_float(INF);
                 __syncwarp();
                 cs3_emit_closeness<DT>(p, l_id, l_cost, min(32u, R - b0), wt, cycles_wt, rankf, n_ri);
-                // their own-side interiors, link by link
-                const uint32_t maxdeg = __reduce_max_sync(CS_FULL, deg);
+                // their own-side interiors, link by link (when betweenness runs too, P5 stages the same nodes and
+                // scatters their closeness terms there)
+                const uint32_t maxdeg = p.betweenness ? 0u : __reduce_max_sync(CS_FULL, deg);
                 for (uint32_t j = 0; j < maxdeg; ++j) {
                     const uint32_t T = j < deg ? (uint32_t)(info8 >> (8 * j)) & 15u : 0u;
                     uint32_t inc = T;
@@ -1012,8 +1014,28 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                             const uint32_t en = e0 + lane;
                             if (en < total) {
                                 const float cost = s_cst[en];
-                                const double pc = __ldg(&p.eligible[s_ids[en]]) ? 0.5 : 1.0;
+                                const uint32_t nid = s_ids[en];
+                                const double pc = __ldg(&p.eligible[nid]) ? 0.5 : 1.0;
                                 s_pcs[en] = (float)pc;
+                                if (p.closeness) {
+                                    // the closeness terms of the same node (P4 leaves the interiors to this pass when both
+                                    // metric families run): centrality.rs:1755-1777, f32 terms
+                                    double* base = p.acc_c + nid;
+                                    const double far_t = (double)__fmul_rn(cost, wt);
+                                    const double harm_t = (double)__fmul_rn(__fdiv_rn(1.0f, cost), wt);
+#pragma unroll
+                                    for (int i = 0; i < DT; ++i) {
+                                        if (i < D && cost <= p.dist_f[i]) {
+                                            ++n_ri;
+                                            double* q = base + (size_t)(5 * i) * g.n;
+                                            cs_red_add(q, (double)wt);
+                                            cs_red_add(q + g.n, far_t);
+                                            cs_red_add(q + 2 * (size_t)g.n, (double)__fmul_rn(rankf[i], cycles_wt));
+                                            cs_red_add(q + 3 * (size_t)g.n, harm_t);
+                                            cs_red_add(q + 4 * (size_t)g.n, (double)__fmul_rn(expf(__fmul_rn(-p.beta_f[i], cost)), wt));
+                                        }
+                                    }
+                                }
                                 if (p.beta_chain) {
                                     // beta_i = 2 * beta_{i+1} exactly (e.g. 500 / 1000 / 2000 m): exp(-beta_i c) is the square
                                     // of exp(-beta_{i+1} c) to within an ulp or two
