@@ -237,10 +237,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
     uint32_t* bins = reinterpret_cast<uint32_t*>(s_warp);
     uint32_t* l_id = bins;
     float* l_cost = reinterpret_cast<float*>(bins + CS3_LIST);
-    float* s_cc = reinterpret_cast<float*>(bins);  // P3 candidates [32 junctions][8 links]
-    uint32_t* s_cd = bins + 256;
-    uint32_t* s_cu = bins + 512;
-    uint32_t* s_cr = bins + 768;
+    uint8_t* s_llist2 = reinterpret_cast<uint8_t*>(bins);  // P3: the chunk's links owned by their junction
     uint32_t* s_ids = bins;                        // P5 staged nodes
     float* s_cst = reinterpret_cast<float*>(bins + NB);
     float* s_pcs = reinterpret_cast<float*>(bins + 2 * NB);
@@ -258,7 +255,9 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
     const CsWarpArena A = cs_arena(p.arena, p.lay, worker);
     uint8_t* linfo = A.bdone;          // [rcap][8] link bytes: T | tie2 << 4 | yhas << 5
     uint32_t* minsucc = A.node_list;   // [rcap] after P2: smallest rank that has this junction as a predecessor
-    uint32_t* frank = reinterpret_cast<uint32_t*>(p.arena + (size_t)worker * p.lay.stride + p.lay.frank);  // [rcap][8]
+    // [rcap][8] per link: {candidate seconds bits, neighbour's seconds bits (inf = no candidate), neighbour id | pos << 28,
+    // rank of the far junction}, written by the link's OWNER end (the earlier-settled one) for both ends
+    uint4* cand = reinterpret_cast<uint4*>(p.arena + (size_t)worker * p.lay.stride + p.lay.frank);
     uint32_t* needm = reinterpret_cast<uint32_t*>(p.arena + (size_t)worker * p.lay.stride + p.lay.needm);  // [rcap]
     const CsV3Graph& g = p.g;
     const uint32_t J = g.J;
@@ -583,10 +582,43 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
             __syncwarp();
             for (uint32_t j = 0; j < deg; ++j) s_llist[inc - deg + j] = (uint16_t)(lane | (j << 5));
             __syncwarp();
+            // every chain is evaluated once, by its OWNER end: the earlier-settled junction (or the only reached one);
+            // first pass: find the owned links of the chunk
+            uint32_t nown = 0;
             for (uint32_t base = 0; base < totalL; base += 32) {
                 const uint32_t e = base + lane;
                 const bool act = e < totalL;
                 const uint32_t code = act ? s_llist[e] : 0u;
+                const uint32_t jl = code & 31u, j = code >> 5;
+                const uint32_t lv = __shfl_sync(CS_FULL, v, jl), loff = __shfl_sync(CS_FULL, off, jl);
+                bool own = false;
+                if (act) {
+                    uint32_t far, paf;
+                    if (lv == J) {
+                        far = j == 0 ? S.A : S.B;
+                        paf = j == 0 ? S.posA : S.posB;
+                    } else {
+                        const uint4 L = __ldg(&g.links[loff + j]);
+                        far = L.x;
+                        paf = (L.w >> 5) & 15u;
+                        if (S.interior && (L.w & 15u) > 0 && L.y == S.soff) {
+                            far = J;
+                            paf = (L.w >> 4) & 1u;
+                        }
+                    }
+                    const uint2 dF = cs_ld(&A.ds[far]);
+                    const uint32_t lr = b0 + jl;
+                    own = dF.x == INF || lr < dF.y || (lr == dF.y && j < paf);
+                }
+                const uint32_t m = __ballot_sync(CS_FULL, own);
+                if (own) s_llist2[nown + __popc(m & ltmask)] = (uint8_t)code;
+                nown += __popc(m);
+            }
+            __syncwarp();
+            for (uint32_t base = 0; base < nown; base += 32) {
+                const uint32_t e = base + lane;
+                const bool act = e < nown;
+                const uint32_t code = act ? s_llist2[e] : 0u;
                 const uint32_t jl = code & 31u, j = code >> 5;
                 const uint32_t lv = __shfl_sync(CS_FULL, v, jl), loff = __shfl_sync(CS_FULL, off, jl);
                 const uint32_t lvid = __shfl_sync(CS_FULL, vid, jl), lavb = __shfl_sync(CS_FULL, avb, jl);
@@ -599,12 +631,12 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                 const uint2 dF = cs_ld(&A.ds[V.far]);
                 const uint32_t fid = V.far == J ? S.id : V.far;
                 // Both waves at once: my front starts at v, theirs at F; the smaller front advances (the settle order of
-                // the chain's nodes), until the fronts meet or neither may advance (cutoff, centrality.rs:1407).
+                // the chain's nodes), until the fronts meet or neither may advance (cutoff, centrality.rs:1407).  The owner
+                // settles first, so it wins exact ties and counts the shared piece.
                 const bool f_reached = dF.x != INF;
-                const bool wins = !f_reached || dF.y > lr || (dF.y == lr && j < V.paf);  // exact ties, shared pieces
                 float a = av, a_prev = av;                    // distance of m_T (v when T == 0) and of the node before it
                 float b = __uint_as_float(dF.x), b_prev = b;  // distance of m_{k+1-jn} (F when jn == 0) and the one before
-                float a_next = __fadd_rn(a, CS3_CB(V.sv));    // my candidate for m_{T+1}
+                float a_next = __fadd_rn(a, CS3_CB(V.sv));    // my candidate for m_{T+1} (for F itself once T == k)
                 float b_next = f_reached ? __fadd_rn(b, CS3_CB(V.sF)) : __uint_as_float(INF);  // theirs for m_{k-jn}
                 uint32_t T = 0, jn = 0;
                 while (T + jn < k) {
@@ -613,55 +645,40 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                     if (!a_ok && !b_ok) break;
                     bool take_a = a_ok;
                     if (a_ok && b_ok)  // the last unsettled node is claimed from both sides; otherwise two different nodes
-                        take_a = T + jn + 1 == k ? (a_next < b_next || (a_next == b_next && wins)) : a_next <= b_next;
+                        take_a = a_next <= b_next;
+                    float settled;
                     if (take_a) {
                         if (a_next == a) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
                         a_prev = a;
                         a = a_next;
                         ++T;
-                        if (p.closeness) {
-                            const int th = cs3_first_threshold<DT>(p, __fmul_rn(a, p.speed));
-                            // a node and the piece (m_{T-1}, m_T), whose larger cost is m_T's
-                            if constexpr (DT <= 3) {
-                                cntNE += 1ull << (16 * th);
-                            } else {
-                                atomicAdd(&histN[th], 1u);
-                                atomicAdd(&histE[th], 1u);
-                            }
-                        }
+                        settled = a;
                         a_next = __fadd_rn(a, CS3_CB(V.sv + T));
                     } else {
                         if (b_next == b) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
                         b_prev = b;
                         b = b_next;
                         ++jn;
+                        settled = b;
                         b_next = __fadd_rn(b, CS3_CB(V.sF + jn));
                     }
-                }
-                n_interior += T;
-                // the neighbour on this link (m_1, or F itself) as a candidate predecessor of v: only when the wave from F
-                // took the whole chain; its candidate is the next step of that wave
-                uint32_t c_ud = INF;
-                float c_c = 0.f;
-                const uint32_t uid = k == 0 ? fid : V.id1;
-                if (f_reached && jn == k && lr != 0) {
-                    const uint32_t ud = __float_as_uint(b);
-                    const bool before = k == 0 ? (dF.y < lr) : cs3_before(g, S, ud, uid, lavb, lvid);
-                    if (before && (p.phase2 || !(b_next > p.max_seconds))) {
-                        c_ud = ud;
-                        c_c = b_next;
+                    if (p.closeness) {
+                        // a node and the piece towards its own end, whose larger cost is the node's
+                        const int th = cs3_first_threshold<DT>(p, __fmul_rn(settled, p.speed));
+                        if constexpr (DT <= 3) {
+                            cntNE += 1ull << (16 * th);
+                        } else {
+                            atomicAdd(&histN[th], 1u);
+                            atomicAdd(&histE[th], 1u);
+                        }
                     }
                 }
-                s_cc[jl * 8 + j] = c_c;
-                s_cd[jl * 8 + j] = c_ud;
-                s_cu[jl * 8 + j] = uid | (V.paf << 28);
-                s_cr[jl * 8 + j] = dF.y;  // sigma of the neighbour = sigma of F (one-predecessor run)
-                cs_st(&frank[(size_t)lr * 8 + j], dF.y);
+                n_interior += T + jn;
                 uint32_t flags = 0;
                 // meeting pair X = m_T (v when T == 0), Y = m_{T+1} (F when T == k): Y is reached iff the fronts met
                 if (f_reached && T + jn == k) {
                     const uint32_t yd = __float_as_uint(b);
-                    if (p.closeness && V.cnt && (dF.y > lr || (dF.y == lr && j < V.paf))) {
+                    if (p.closeness && V.cnt) {
                         const float ec = __fmul_rn(fmaxf(a, b), p.speed);
                         const int th = cs3_first_threshold<DT>(p, ec);
                         if constexpr (DT <= 3) cntE += (unsigned long long)V.cnt << (16 * th);
@@ -682,7 +699,28 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                         if (cs3_other_kept(b, a_next, own_first, p.phase2 != 0, one_plus_tol, p.max_seconds)) flags |= 0x20u;
                     }
                 }
-                s_info[jl * 8 + j] = (uint8_t)(T | flags);
+                // this end: the owner settles before F and before every node reached from F, so the link offers it no
+                // candidate predecessor
+                cs_st(&cand[(size_t)lr * 8 + j], make_uint4(0u, INF, 0u, dF.y));
+                cs_st(&linfo[(size_t)lr * 8 + j], (uint8_t)(T | flags));
+                if (f_reached) {
+                    // the far end: it owns jn interiors, the roles of the two meeting flags swap, and the neighbour on its side
+                    // of the link (m_k, or this junction) is its candidate predecessor when my wave took the whole chain
+                    uint32_t c_ud = INF;
+                    float c_c = 0.f;
+                    const uint32_t nid = k == 0 ? lvid : V.id1 + V.step * (int)(k - 1);
+                    if (T == k && dF.y != 0) {
+                        const uint32_t ud = __float_as_uint(a);
+                        const bool before = k == 0 ? true : cs3_before(g, S, ud, nid, dF.x, fid);
+                        if (before && (p.phase2 || !(a_next > p.max_seconds))) {
+                            c_ud = ud;
+                            c_c = a_next;
+                        }
+                    }
+                    const uint32_t fflags = ((flags & 0x10u) ? 0x20u : 0u) | ((flags & 0x20u) ? 0x10u : 0u);
+                    cs_st(&cand[(size_t)dF.y * 8 + V.paf], make_uint4(__float_as_uint(c_c), c_ud, nid | (j << 28), lr));
+                    cs_st(&linfo[(size_t)dF.y * 8 + V.paf], (uint8_t)(jn | fflags));
+                }
             }
             __syncwarp();
             // P3b: the junction's candidates in settle order of the neighbours, then the sequential rule
@@ -692,13 +730,11 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
             uint32_t pmask_c = 0;
             if (valid) {
                 const float av = __uint_as_float(avb);
-                unsigned long long info8 = 0ull;
                 for (uint32_t j = 0; j < deg; ++j) {
-                    info8 |= (unsigned long long)s_info[lane * 8 + j] << (8 * j);
-                    const uint32_t ud = s_cd[lane * 8 + j];
+                    const uint4 cd4 = cs_ld(&cand[(size_t)r * 8 + j]);
+                    const uint32_t ud = cd4.y;
                     if (ud == INF) continue;
-                    const uint32_t uidp = s_cu[lane * 8 + j];
-                    const uint32_t uid = uidp & 0x0fffffffu, paf = uidp >> 28;
+                    const uint32_t uid = cd4.z & 0x0fffffffu, paf = cd4.z >> 28;
                     int q = ncand++;
                     while (q > 0) {
                         const bool gt = cd[q - 1] != ud ? cd[q - 1] > ud
@@ -712,13 +748,12 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                         cj[q] = cj[q - 1];
                         --q;
                     }
-                    cc[q] = s_cc[lane * 8 + j];
+                    cc[q] = __uint_as_float(cd4.x);
                     cu[q] = uid;
                     cd[q] = ud;
-                    crk[q] = s_cr[lane * 8 + j];
+                    crk[q] = cd4.w;
                     cj[q] = j | (paf << 8);
                 }
-                cs_st(reinterpret_cast<unsigned long long*>(linfo + (size_t)r * 8), info8);
                 if (ncand == 1 && !p.phase2) {
                     pmask_c = 1u;
                 } else if (!p.phase2) {
@@ -939,7 +974,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                         // F continues the path through this link iff F chose it as a predecessor (P3b left the bit)
                         const bool needF = (lnm >> j) & 1u;
                         work = T > 0 || needF || yhas;
-                        const uint32_t rankF = (needF || yhas || tie2) ? cs_ld(&frank[(size_t)lr * 8 + j]) : 0u;
+                        const uint32_t rankF = (needF || yhas || tie2) ? cs_ld(&cand[(size_t)lr * 8 + j].w) : 0u;
                         if (work) V = cs3_view(g, S, lw, loff, j);
                         const uint32_t k = V.k;
                         double sigma_F = 0.0;
