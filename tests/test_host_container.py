@@ -187,3 +187,17 @@ def test_wrap_progress_polls_and_reraises():
 
     with pytest.raises(ValueError, match="dual graph"):
         config.wrap_progress(3, Fake(), boom)
+
+
+def test_od_matrix_semantics():
+    # centrality.rs:54-91: parallel arrays -> {origin: {destination: weight}}, a repeated pair keeps the last weight
+    from cityseer_b200.rustalgos.centrality import OdMatrix
+
+    od = OdMatrix([0, 0, 1, 0], [1, 2, 2, 1], [1.0, 2.0, 3.0, 5.5])
+    assert od.len() == 3 and od.n_origins() == 2
+    assert od.map[0][1] == 5.5 and od.map[1][2] == 3.0
+    with pytest.raises(ValueError, match="must have equal length"):
+        OdMatrix([0, 1], [1], [1.0, 2.0])
+    with pytest.raises(OverflowError):
+        OdMatrix([-1], [1], [1.0])
+    assert OdMatrix([], [], []).len() == 0
