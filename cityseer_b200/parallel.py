@@ -83,5 +83,9 @@ def centrality_shortest_sharded(ns, distances=None, betas=None, minutes=None, co
         return out
 
     total = sharded_sum(compute, sources, wt, group)
-    host = total.cpu().numpy()
-    return _c.CentralityShortestResult(d, ns.node_keys_py(), ns.frozen().node_indices, host, stats_box)
+    # download into a pooled page-locked buffer (full PCIe rate; every rank has its own link)
+    from . import _native
+
+    host = _native.pinned_empty(_native.load_library(), tuple(total.shape))
+    torch.from_numpy(host).copy_(total)
+    return _c.CentralityShortestResult(d, ns._node_keys_shared(), ns.frozen().node_indices, host, stats_box)
