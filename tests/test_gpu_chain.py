@@ -161,3 +161,38 @@ def test_one_way_piece_uses_the_arena_kernel(oracle_mod):
     d, b, s = H.pair(distances=[300])
     ref, _ = oracle_mod.OracleGraph(ns.frozen()).centrality_shortest(d, b, s, H.SPEED, n_threads=2)
     np.testing.assert_allclose(res._out, ref, rtol=RTOL, atol=1e-7)
+
+
+def test_full_size_cfg4_properties_and_kernel_agreement():
+    """BASELINE config #4 at full size (1 027 753 nodes): the oracle would need hours, so the chain kernel is checked
+    through size-independent properties and against the independently written arena kernel on the same sources."""
+    from cityseer_b200 import _native
+
+    ns, _ = synth.config("cfg4")
+    f = ns.frozen()
+    rng = np.random.default_rng(5)
+    picks = rng.choice(f.node_indices, 12288, replace=False)
+    a_src, b_src = np.sort(picks[:6144]), np.sort(picks[6144:])
+    kw = dict(distances=[500, 1000, 2000], sample_probability=1.0, pbar_disabled=True)
+    ra = ns.centrality_shortest(source_indices=a_src.tolist(), **kw)
+    rb = ns.centrality_shortest(source_indices=b_src.tolist(), **kw)
+    rab = ns.centrality_shortest(source_indices=np.sort(picks).tolist(), compute_betweenness=False, **kw)
+    assert ra.stats["kernel_used"] == 3 and rab.stats["kernel_used"] == 3
+    # linearity over disjoint source sets (closeness does not depend on which nodes are sources)
+    assert np.array_equal(ra._out[0] + rb._out[0], rab._out[0])
+    assert np.array_equal(ra._out[2] + rb._out[2], rab._out[2])
+    np.testing.assert_allclose(ra._out[1] + rb._out[1], rab._out[1], rtol=1e-9)
+    np.testing.assert_allclose(ra._out[3:5] + rb._out[3:5], rab._out[3:5], rtol=1e-9)
+    # checksum: the density column sums are the per-threshold reachable-target totals counted on the device
+    assert [int(x) for x in ra._out[0].sum(axis=1)] == ra.reachability_totals
+    # thresholds nest: anything within 500 m is within 1000 m is within 2000 m
+    assert np.all(ra._out[0][0] <= ra._out[0][1]) and np.all(ra._out[0][1] <= ra._out[0][2])
+    # the arena kernel, written independently, on the same sources: counts bit-exact, floats to summation order
+    _native.DEFAULT_OPTIONS["kernel"] = 1.0
+    ns2, _ = synth.config("cfg4")
+    r1 = ns2.centrality_shortest(source_indices=a_src.tolist(), **kw)
+    assert r1.stats["kernel_used"] == 1
+    assert np.array_equal(r1._out[0], ra._out[0]) and np.array_equal(r1._out[2], ra._out[2])
+    np.testing.assert_allclose(r1._out, ra._out, rtol=1e-9, atol=1e-9)
+    for key in ("settled", "edge_iters", "sum_ri", "sum_ci"):
+        assert r1.stats[key] == ra.stats[key], key
