@@ -25,6 +25,9 @@
 #ifndef CS3_PHASE_SYNC
 #define CS3_PHASE_SYNC 1
 #endif
+#ifndef CS3_NB3
+#define CS3_NB3 128u  // staged nodes per sub-iteration of the dependency pass, up to three thresholds
+#endif
 #define CS3_LIST 512      // staged (node, cost) entries per warp for the packed closeness scatter
 
 struct CsV3Graph {
@@ -218,7 +221,7 @@ template <int DT>
 __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3(const CsShortest3Params p) {
     // per-warp shared memory: region A (4 KB): P2 bins | P3 candidates | P4 staged (node, cost) list | P5 node ids / costs;
     // region B (6 KB): P3 walk values | P5 per-node seeds -> credits; region C: P3 / P5 link list, link bytes, P5 outflow
-    constexpr uint32_t NB = DT <= 3 ? 128u : DT == 4 ? 96u : 24u;  // staged nodes per P5 sub-iteration
+    constexpr uint32_t NB = DT <= 3 ? CS3_NB3 : DT == 4 ? 96u : 24u;  // staged nodes per P5 sub-iteration
     constexpr uint32_t WALK_BYTES = (CS3_KMAX + 2 + 28) * 32 * 4;
     constexpr uint32_t BYTES_A = CS_NBINS * 4, BYTES_B = 2 * DT * NB * 8 > WALK_BYTES ? 2 * DT * NB * 8 : WALK_BYTES;
     constexpr uint32_t BYTES_C = 2 * DT * 32 * 8 + 256 * 2 + 256;
@@ -1233,7 +1236,7 @@ __global__ void cs_k_epilogue_shortest3(const double* __restrict__ acc_c, const 
 
 template <int DT>
 static constexpr uint32_t cs3_smem_bytes() {
-    constexpr uint32_t NB = DT <= 3 ? 128u : DT == 4 ? 96u : 24u;
+    constexpr uint32_t NB = DT <= 3 ? CS3_NB3 : DT == 4 ? 96u : 24u;
     constexpr uint32_t WALK_BYTES = (CS3_KMAX + 2 + 28) * 32 * 4;
     constexpr uint32_t B = 2 * DT * NB * 8 > WALK_BYTES ? 2 * DT * NB * 8 : WALK_BYTES;
     return CS3_WARPS * (CS_NBINS * 4 + B + 2 * DT * 32 * 8 + 256 * 2 + 256);
