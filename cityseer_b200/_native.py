@@ -93,6 +93,15 @@ SIGNATURES = {
     "cs_dijkstra_tree_shortest": (
         C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, _u32p, _u32p, C.POINTER(C.c_int64), _f32p],
     ),
+    "cs_dijkstra_tree_segment": (
+        C.c_int,
+        [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, _u32p, _u32p, _u64p, _u32p, C.POINTER(C.c_int64), _f32p,
+         C.POINTER(C.c_int64), C.POINTER(C.c_int64), _u8p],
+    ),  # fmt: skip
+    "cs_dijkstra_tree_simplest": (
+        C.c_int,
+        [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, _u32p, _u32p, C.POINTER(C.c_int64), _f32p, _f32p, _u8p],
+    ),  # fmt: skip
     "cs_progress": (C.c_uint64, [C.c_void_p]),
     "cs_shortest_search": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _f32p, _f64p, _u32p]),
 }
@@ -189,6 +198,7 @@ class DeviceGraph:
         self.device = current_device() if device is None else int(device)
         f = frozen
         self.node_bound = int(f.node_bound)
+        self.edge_bound = int(f.edge_bound)
         self._h = lib.cs_graph_create(
             f.node_bound, _ptr(f.node_exists, _u8p), _ptr(f.live, _u8p), _ptr(f.weight, _f32p),
             None if getattr(f, "xs", None) is None else _ptr(f.xs, _f64p),
@@ -384,21 +394,41 @@ class DeviceGraph:
         return agg, sig, npred
 
     def dijkstra_tree(self, kind: int, src_idx: int, max_seconds: int, speed: float):
-        """kind 0 = dijkstra_tree_shortest: (visited order, predecessor per node (-1 none), seconds per node)."""
-        if kind != 0:
-            raise NotImplementedError(
-                "dijkstra_tree_simplest / dijkstra_tree_segment (single-source dumps) are the next row of the scope table "
-                "(SURVEY.md §8f-3); dijkstra_tree_shortest is served by the device"
-            )
+        """Single-source tree dumps.  kind 0 = dijkstra_tree_shortest: (visited order, pred per node (-1 none), seconds
+        per node); kind 1 = dijkstra_tree_simplest: (visited nodes, pred, simpl_dist, seconds, flags); kind 2 =
+        dijkstra_tree_segment: (visited nodes, visited edge ids, pred, seconds, origin_seg, last_seg, flags)."""
         n = self.node_bound
+        i64p = C.POINTER(C.c_int64)
         nv = C.c_uint32(0)
         order = np.zeros(max(n, 1), np.uint32)
         pred = np.zeros(max(n, 1), np.int64)
         agg = np.zeros(max(n, 1), np.float32)
         with self._call_lock:
-            rc = self._lib.cs_dijkstra_tree_shortest(self._h, int(src_idx), int(max_seconds), float(speed), C.byref(nv),
-                                                     _ptr(order, _u32p), pred.ctypes.data_as(C.POINTER(C.c_int64)),
-                                                     _ptr(agg, _f32p))  # fmt: skip
-            if rc:
-                raise ValueError(_err(self._lib))
-        return order[: nv.value], pred[:n], agg[:n]
+            if kind == 0:
+                rc = self._lib.cs_dijkstra_tree_shortest(self._h, int(src_idx), int(max_seconds), float(speed), C.byref(nv),
+                                                         _ptr(order, _u32p), pred.ctypes.data_as(i64p), _ptr(agg, _f32p))  # fmt: skip
+                if rc:
+                    raise ValueError(_err(self._lib))
+                return order[: nv.value], pred[:n], agg[:n]
+            flags = np.zeros(max(n, 1), np.uint8)
+            if kind == 1:
+                simpl = np.zeros(max(n, 1), np.float32)
+                rc = self._lib.cs_dijkstra_tree_simplest(self._h, int(src_idx), int(max_seconds), float(speed), C.byref(nv),
+                                                         _ptr(order, _u32p), pred.ctypes.data_as(i64p), _ptr(simpl, _f32p),
+                                                         _ptr(agg, _f32p), _ptr(flags, _u8p))  # fmt: skip
+                if rc:
+                    raise ValueError(_err(self._lib))
+                return order[: nv.value], pred[:n], simpl[:n], agg[:n], flags[:n]
+            if kind == 2:
+                ne = C.c_uint64(0)
+                eorder = np.zeros(max(self.edge_bound, 1), np.uint32)
+                origin = np.zeros(max(n, 1), np.int64)
+                last = np.zeros(max(n, 1), np.int64)
+                rc = self._lib.cs_dijkstra_tree_segment(self._h, int(src_idx), int(max_seconds), float(speed), C.byref(nv),
+                                                        _ptr(order, _u32p), C.byref(ne), _ptr(eorder, _u32p),
+                                                        pred.ctypes.data_as(i64p), _ptr(agg, _f32p), origin.ctypes.data_as(i64p),
+                                                        last.ctypes.data_as(i64p), _ptr(flags, _u8p))  # fmt: skip
+                if rc:
+                    raise ValueError(_err(self._lib))
+                return order[: nv.value], eorder[: ne.value], pred[:n], agg[:n], origin[:n], last[:n], flags[:n]
+        raise ValueError(f"unknown tree kind {kind}")

@@ -14,6 +14,7 @@
 #include "cs_shortest3.cuh"
 #include "cs_segment.cuh"
 #include "cs_simplest.cuh"
+#include "cs_tree.cuh"
 
 // ------------------------------------------------------------------------------------------------ error handling
 static thread_local std::string g_err;
@@ -99,6 +100,7 @@ struct cs_graph {
     int opt_kernel = 0;  // 0 auto (chain-contracted kernel when the graph qualifies, else the global-arena kernel),
                          // 1 global-arena kernel, 3 chain-contracted kernel (required)
     float opt_delta_factor = 12.0f;
+    std::vector<uint32_t> in_edge_at;  // container edge id stored at each in-CSR position (tree dumps report edge ids)
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -382,6 +384,8 @@ extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_ex
     g->dual_status = dual_status;
     g->twin_missing = twin_missing;
     g->mean_edge_len = E ? (float)(len_sum / (double)E) : 1.0f;
+    g->in_edge_at.resize(E);
+    for (uint32_t e : order) g->in_edge_at[in_slot[e]] = e;
     cudaDeviceProp prop;
     CS_CUDA_NULL(cudaGetDeviceProperties(&prop, device));
     g->sm_count = prop.multiProcessorCount;
@@ -1047,3 +1051,4 @@ extern "C" int cs_shortest_search(cs_graph* g, uint32_t src, uint32_t max_second
 
 // ------------------------------------------------------------------------------------------------ segment / simplest
 #include "cs_api_more.inl"
+#include "cs_api_tree.inl"

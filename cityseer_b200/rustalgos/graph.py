@@ -922,9 +922,43 @@ class NetworkStructure:
                 "cityseer.tools.graphs.nx_to_dual(...) before ingesting it into NetworkStructure."
             )
         self._validate_dijkstra_inputs(src_idx, float(speed_m_s))
-        return self.device_graph().dijkstra_tree(1, src_idx, int(max_seconds), float(np.float32(speed_m_s)))
+        order, pred, simpl, agg, flags = self.device_graph().dijkstra_tree(
+            1, src_idx, int(max_seconds), float(np.float32(speed_m_s))
+        )
+        tree_map = [NodeVisit() for _ in range(len(pred))]
+        for i in np.nonzero(flags)[0].tolist():
+            t = tree_map[i]
+            t.visited = bool(flags[i] & 1)
+            t.discovered = bool(flags[i] & 2)
+            t.pred = None if pred[i] < 0 else int(pred[i])
+            t.simpl_dist = float(simpl[i])
+            t.agg_seconds = float(agg[i])
+        return order.tolist(), tree_map
 
     def dijkstra_tree_segment(self, src_idx: int, max_seconds: int, speed_m_s: float):
-        """centrality.rs:1523-1611"""
+        """centrality.rs:1523-1611 — returns ``(visited_nodes, visited_edges, tree_map, edge_map)``."""
         self._validate_dijkstra_inputs(src_idx, float(speed_m_s))
-        return self.device_graph().dijkstra_tree(2, src_idx, int(max_seconds), float(np.float32(speed_m_s)))
+        speed = np.float32(speed_m_s)
+        order, eorder, pred, agg, origin, last, flags = self.device_graph().dijkstra_tree(
+            2, src_idx, int(max_seconds), float(speed)
+        )
+        tree_map = [NodeVisit() for _ in range(len(pred))]
+        short = agg * speed  # f32 product, as total_seconds * speed_m_s (:1593)
+        for i in np.nonzero(flags)[0].tolist():
+            t = tree_map[i]
+            t.visited = bool(flags[i] & 1)
+            t.discovered = bool(flags[i] & 2)
+            t.pred = None if pred[i] < 0 else int(pred[i])
+            t.agg_seconds = float(agg[i])
+            t.short_dist = float(short[i])
+            t.origin_seg = None if origin[i] < 0 else int(origin[i])
+            t.last_seg = None if last[i] < 0 else int(last[i])
+        f = self.frozen()
+        edge_map = [EdgeVisit() for _ in range(f.edge_bound)]
+        for eid in eorder.tolist():
+            ev = edge_map[eid]
+            ev.visited = True
+            ev.start_nd_idx = int(f.dst[eid])  # the settled node the edge points into (:1561, :1570)
+            ev.end_nd_idx = int(f.src[eid])
+            ev.edge_idx = int(f.edge_idx[eid])
+        return order.tolist(), eorder.tolist(), tree_map, edge_map

@@ -141,6 +141,24 @@ int cs_betweenness_od_shortest(cs_graph* g, int D, const uint32_t* distances, co
 int cs_dijkstra_tree_shortest(cs_graph* g, uint32_t src, uint32_t max_seconds, float speed_m_s, uint32_t* n_visited,
                               uint32_t* visited_order, int64_t* pred, float* agg_seconds);
 
+/* Replaces NetworkStructure.dijkstra_tree_segment (centrality.rs:1523-1611): the single-predecessor tree of one capped
+ * search over incoming edges with the visited-edge list.  `visited_nodes[0 .. *n_visited)` in pop order;
+ * `visited_edges[0 .. *n_visited_edges)` are container edge ids (petgraph EdgeIndex) in the order the reference pushes
+ * them (the caller fills EdgeVisit.start_nd_idx = the edge's target, end_nd_idx = its source, edge_idx = its payload
+ * key); per node [node_bound]: pred (-1 none), agg_seconds (inf = not reached), origin_seg / last_seg (edge ids,
+ * -1 none), flags (bit 0 visited, bit 1 discovered).  visited_nodes is sized node_bound, visited_edges edge_bound. */
+int cs_dijkstra_tree_segment(cs_graph* g, uint32_t src, uint32_t max_seconds, float speed_m_s, uint32_t* n_visited,
+                             uint32_t* visited_nodes, uint64_t* n_visited_edges, uint32_t* visited_edges, int64_t* pred,
+                             float* agg_seconds, int64_t* origin_seg, int64_t* last_seg, uint8_t* flags);
+
+/* Replaces NetworkStructure.dijkstra_tree_simplest (centrality.rs:1510-1521, dijkstra_tree_angular :1202-1332): the
+ * doubled-state angular search collapsed to its node-level tree.  `visited_nodes` lists nodes in first-reached order
+ * (the source first); per node [node_bound]: pred (-1 none), simpl_dist (summed angle, inf = not reached),
+ * agg_seconds, flags (bit 0 visited, bit 1 discovered).  Fails on a primal graph like the reference. */
+int cs_dijkstra_tree_simplest(cs_graph* g, uint32_t src, uint32_t max_seconds, float speed_m_s, uint32_t* n_visited,
+                              uint32_t* visited_nodes, int64_t* pred, float* simpl_dist, float* agg_seconds,
+                              uint8_t* flags);
+
 /* Replaces NetworkStructure.progress() (graph.rs:413): sources finished by the call in flight on this graph
  * (readable from another host thread while a compute call blocks). */
 uint64_t cs_progress(cs_graph* g);

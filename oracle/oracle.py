@@ -210,6 +210,27 @@ class OracleGraph:
     def dijkstra_tree_simplest(self, src, max_seconds, speed):
         return self._tree(lib().orc_dijkstra_tree_simplest, src, max_seconds, speed)
 
+    def dijkstra_tree_segment(self, src, max_seconds, speed):
+        """(visited_nodes, visited_edges, tree_map, edge_map) of centrality.rs:1523-1611; edge_map entries are
+        (visited, start_nd_idx, end_nd_idx, edge_idx) tuples with None for unset fields."""
+        nb, eb = self.nb, self.eb
+        visited = np.zeros(max(nb, 1), np.uint32)
+        ve = np.zeros(max(eb, 1), np.uint32)
+        nv, ne = C.c_uint64(0), C.c_uint64(0)
+        pred, os_, ls = (np.zeros(nb, np.int64) for _ in range(3))
+        sd, sm, ag = (np.zeros(nb, np.float32) for _ in range(3))
+        fl = np.zeros(nb, np.uint8)
+        es, ee, ei = (np.zeros(max(eb, 1), np.int64) for _ in range(3))
+        ev = np.zeros(max(eb, 1), np.uint8)
+        lib().orc_dijkstra_tree_segment(self._h, src, max_seconds, speed, _p(visited, _u32p), C.byref(nv), _p(ve, _u32p),
+                                        C.byref(ne), _p(pred, _i64p), _p(sd, _f32p), _p(sm, _f32p), _p(ag, _f32p),
+                                        _p(os_, _i64p), _p(ls, _i64p), _p(fl, _u8p), _p(es, _i64p), _p(ee, _i64p),
+                                        _p(ei, _i64p), _p(ev, _u8p))  # fmt: skip
+        opt = lambda x: None if x < 0 else int(x)  # noqa: E731
+        edge_map = [(bool(ev[i]), opt(es[i]), opt(ee[i]), opt(ei[i])) for i in range(eb)]
+        return (visited[: nv.value].tolist(), ve[: ne.value].tolist(), self._tree_map(pred, sd, sm, ag, os_, ls, fl),
+                edge_map)  # fmt: skip
+
     def shortest_distances(self, src, max_seconds, speed):
         nb = self.nb
         agg = np.zeros(nb, np.float32)

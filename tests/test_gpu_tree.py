@@ -50,5 +50,88 @@ def test_tree_errors():
         ns.dijkstra_tree_shortest(9999, 600, H.SPEED)
     with pytest.raises(ValueError, match="finite and positive"):
         ns.dijkstra_tree_shortest(0, 600, 0.0)
-    with pytest.raises(NotImplementedError):
-        ns.dijkstra_tree_segment(0, 600, H.SPEED)
+    with pytest.raises(ValueError, match="out of range"):
+        ns.dijkstra_tree_segment(9999, 600, H.SPEED)
+    with pytest.raises(ValueError, match="dual graph"):
+        ns.dijkstra_tree_simplest(0, 600, H.SPEED)
+
+
+def _feq(a, b):
+    return np.float32(a) == np.float32(b) or (np.isinf(a) and np.isinf(b))
+
+
+def compare_segment(oracle_mod, ns, src, max_seconds):
+    """dijkstra_tree_segment (centrality.rs:1523-1611): the device replays the reference's heap, so node order, edge
+    order, origin / last segments and the edge map are compared exactly."""
+    vn, ve, tree, emap = ns.dijkstra_tree_segment(src, max_seconds, H.SPEED)
+    ovn, ove, otree, oemap = oracle_mod.OracleGraph(ns.frozen()).dijkstra_tree_segment(src, max_seconds, H.SPEED)
+    assert vn == ovn
+    assert ve == ove
+    assert len(tree) == len(otree) and len(emap) == len(oemap)
+    for i, (a, b) in enumerate(zip(tree, otree)):
+        assert (a.visited, a.discovered, a.pred, a.origin_seg, a.last_seg) == (
+            b.visited, b.discovered, b.pred, b.origin_seg, b.last_seg), i  # fmt: skip
+        assert _feq(a.agg_seconds, b.agg_seconds) and _feq(a.short_dist, b.short_dist), i
+        assert np.isinf(a.simpl_dist)
+    for i, (a, b) in enumerate(zip(emap, oemap)):
+        assert (a.visited, a.start_nd_idx, a.end_nd_idx, a.edge_idx) == b, i
+    return len(vn), len(ve)
+
+
+def compare_simplest(oracle_mod, ns, src, max_seconds):
+    """dijkstra_tree_simplest (centrality.rs:1202-1332), exact replay."""
+    vn, tree = ns.dijkstra_tree_simplest(src, max_seconds, H.SPEED)
+    ovn, otree = oracle_mod.OracleGraph(ns.frozen()).dijkstra_tree_simplest(src, max_seconds, H.SPEED)
+    assert vn == ovn
+    assert len(tree) == len(otree)
+    for i, (a, b) in enumerate(zip(tree, otree)):
+        assert (a.visited, a.discovered, a.pred) == (b.visited, b.discovered, b.pred), i
+        assert _feq(a.agg_seconds, b.agg_seconds) and _feq(a.simpl_dist, b.simpl_dist), i
+        assert a.origin_seg is None and a.last_seg is None and np.isinf(a.short_dist)
+    return len(vn)
+
+
+def test_tree_segment_mock_graph(oracle_mod):
+    _g, _n, _e, ns = H.primal_ns()
+    for src in (0, 7, 23, 49, 56):
+        compare_segment(oracle_mod, ns, src, 600)
+    nn, ne = compare_segment(oracle_mod, ns, 10, 5000)  # the whole component
+    assert nn == 50 and ne > 50
+    assert compare_segment(oracle_mod, ns, 10, 0)[0] == 1  # nothing within reach: the source alone, its edges visited
+
+
+def test_tree_segment_decomposed_grid(oracle_mod):
+    ns, _ = synth.config("cfg4", 0.05)
+    f = ns.frozen()
+    for src in f.node_indices[:: max(1, len(f.node_indices) // 5)][:5].tolist():
+        nn, _ne = compare_segment(oracle_mod, ns, int(src), 900)
+        assert nn > 100
+
+
+def test_tree_segment_after_edits(oracle_mod):
+    # removed nodes / edges leave gaps in the edge ids the dump reports (StableGraph semantics, graph.rs:1017-1033)
+    _g, _n, _e, ns = H.primal_ns()
+    ns.remove_street_node(12)
+    for src in (0, 10, 30):
+        compare_segment(oracle_mod, ns, src, 1200)
+
+
+def test_tree_simplest_mock_dual(oracle_mod):
+    _g, _n, _e, ns = H.dual_ns()
+    f = ns.frozen()
+    for src in f.node_indices[::9].tolist():
+        compare_simplest(oracle_mod, ns, int(src), 600)
+    assert compare_simplest(oracle_mod, ns, int(f.node_indices[3]), 5000) > 40
+
+
+def test_tree_simplest_dual_grid(oracle_mod):
+    ns, _ = synth.config("cfg3", 0.05)
+    f = ns.frozen()
+    for src in f.node_indices[:: max(1, len(f.node_indices) // 5)][:5].tolist():
+        assert compare_simplest(oracle_mod, ns, int(src), 900) > 50
+
+
+def test_tree_simplest_diamond(oracle_mod):
+    _g, _n, _e, ns = H.diamond_ns(dual=True)
+    for src in ns.node_indices():
+        compare_simplest(oracle_mod, ns, int(src), 1000)
