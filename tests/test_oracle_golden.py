@@ -265,3 +265,25 @@ def test_threshold_pairing_tables():
     for dd, (bb, ss) in table.items():
         d, b, s = rustalgos.pair_distances_betas_time(H.SPEED, distances=[dd])
         assert s == [ss] and abs(b[0] - bb) < 1e-7
+
+
+def test_committed_fixture_matches_the_oracle(oracle_mod):
+    # tests/golden/cfg1_mock_graph.npz (made by tests/golden/make_golden.py): BASELINE.json configs[0]
+    import os
+
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg1_mock_graph.npz"))
+    d, b, s = H.pair(distances=[400, 800, 1600])
+    assert fx["distances"].tolist() == list(d) and fx["seconds"].tolist() == list(s)
+    assert np.array_equal(fx["betas"], np.array(b, np.float32))
+    _g, _n, _e, ns = H.primal_ns()
+    f = ns.frozen()
+    og = oracle_mod.OracleGraph(f)
+    out, cnt = og.centrality_shortest(d, b, s, H.SPEED)
+    assert np.array_equal(H.compact(out, f), fx["shortest"])  # same code, same machine arithmetic: bit for bit
+    assert cnt["settled"] == int(fx["settled"]) and cnt["edge_iters"] == int(fx["edge_iters"])
+    seg, _ = og.segment_centrality(d, b, s, H.SPEED)
+    np.testing.assert_allclose(H.compact(seg, f), fx["segment"], rtol=1e-12, atol=0)
+    _gd, _nd, _ed, nsd = H.dual_ns()
+    fd = nsd.frozen()
+    simp, _ = oracle_mod.OracleGraph(fd).centrality_simplest(d, s, H.SPEED, unit=90.0, offset=1.0)
+    np.testing.assert_allclose(H.compact(simp, fd), fx["simplest"], rtol=1e-12, atol=0)
