@@ -499,7 +499,9 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
     rcap = std::max(rcap, 32u);
     const uint32_t qcap = rcap * 2 + 64;
     uint32_t workers = g->cfg_workers ? g->cfg_workers
-                                      : (uint32_t)g->sm_count * (kind == 3 ? CS3_MIN_BLOCKS * CS3_WARPS : CS_MIN_BLOCKS * CS_WARPS_PER_CTA);
+                                      : (uint32_t)g->sm_count * (kind == 3   ? CS3_MIN_BLOCKS * CS3_WARPS
+                                                                 : kind == 1 ? CS_SEG_MIN_BLOCKS * CS_WARPS_PER_CTA
+                                                                             : CS_MIN_BLOCKS * CS_WARPS_PER_CTA);
     workers = std::max<uint32_t>(CS_WARPS_PER_CTA, workers / CS_WARPS_PER_CTA * CS_WARPS_PER_CTA);
     CsArenaLayout L{};
     size_t off = 0;
@@ -559,7 +561,7 @@ static int ensure_arena_angular(cs_graph* g, int D) {
     uint32_t rcap = g->cfg_rcap ? g->cfg_rcap : (1u << 16);
     rcap = (uint32_t)std::min<size_t>(std::max<size_t>(rcap, 64), nstates);
     const uint32_t hcap = rcap * 4 + 64;
-    uint32_t workers = g->cfg_workers ? g->cfg_workers : (uint32_t)g->sm_count * CS_MIN_BLOCKS * CS_WARPS_PER_CTA;
+    uint32_t workers = g->cfg_workers ? g->cfg_workers : (uint32_t)g->sm_count * CS_ANG_MIN_BLOCKS * CS_WARPS_PER_CTA;
     workers = std::max<uint32_t>(CS_WARPS_PER_CTA, workers / CS_WARPS_PER_CTA * CS_WARPS_PER_CTA);
     CsAngLayout L{};
     size_t off = 0;

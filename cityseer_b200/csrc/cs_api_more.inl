@@ -89,7 +89,7 @@ extern "C" int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distanc
         return cs_fail("Edge not found: segment_centrality needs the reverse twin of every directed edge (graph.rs:1291)");
     CS_CUDA(cudaSetDevice(g->device));
     g->last_kernel = 0;
-    if (ensure_arena(g, 0, D)) return 1;
+    if (ensure_arena(g, 1, D)) return 1;
     uint32_t launches = 0;
     CS_CUDA(cudaEventRecord(g->ev[0], g->stream));
     if (stage_sources(g, n_sources, sources, nullptr, nullptr)) return 1;

@@ -105,8 +105,13 @@ __global__ void cs_k_init_ang(uint8_t* arena, size_t stride, size_t ds_off, size
     for (size_t k = i; k < n_nodes; k += step) dn[k] = make_uint2(CS_INF_BITS, CS_INF_BITS);
 }
 
+// resident CTAs per SM: the replayed heap leaves one lane busy for long stretches, so warps are what hides latency
+// (measured on cfg3: 3 CTAs 341 k sources/s, 4: 385 k, 5: 403 k, 6: 406 k, 8: 404 k)
+#ifndef CS_ANG_MIN_BLOCKS
+#define CS_ANG_MIN_BLOCKS 5
+#endif
 template <int DT>
-__global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_simplest(const CsSimplestParams p) {
+__global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_ANG_MIN_BLOCKS) cs_k_simplest(const CsSimplestParams p) {
     const uint32_t lane = cs_lane();
     const uint32_t worker = blockIdx.x * CS_WARPS_PER_CTA + (threadIdx.x >> 5);
     const uint32_t ltmask = cs_lanemask_lt();
