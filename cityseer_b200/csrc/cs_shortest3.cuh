@@ -246,6 +246,8 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
     float* s_pcs = reinterpret_cast<float*>(bins + 2 * NB);
     float* walk = reinterpret_cast<float*>(s_warp + BYTES_A);
     float* cblk = walk + (CS3_KMAX + 2) * 32 + lane;  // the lane's column of the chain-block scratch (28 rows)
+    uint16_t* ttab = reinterpret_cast<uint16_t*>(bins);  // P1: (owner lane | link << 8) of the batch's relaxations
+    static_assert(32 * CS3_MAX_LINKS * 2 <= BYTES_A, "P1 task table must fit region A");
     double* s_crd = reinterpret_cast<double*>(s_warp + BYTES_A);
     double* s_acc = reinterpret_cast<double*>(s_warp + BYTES_A + BYTES_B);
     uint16_t* s_llist = reinterpret_cast<uint16_t*>(s_warp + BYTES_A + BYTES_B + 2 * DT * 32 * 8);
@@ -356,15 +358,36 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                                 deg = ji.y & 0xffu;
                             }
                         }
-                        const uint32_t maxdeg = __reduce_max_sync(CS_FULL, deg);
-                        for (uint32_t j = 0; j < maxdeg; ++j) {
+                        // One lane per LINK: the frontier holds few junctions at a time (about nine per batch on the
+                        // 1M-node street graph), so the (junction, link) pairs of the batch are spread over the lanes and
+                        // relaxed together - link record, chain seconds and atomicMin are three dependent L2 round
+                        // trips per batch instead of three per link of the widest junction.
+                        const uint32_t cnt = deg - (skip < deg ? 1u : 0u);
+                        uint32_t incl = cnt;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t up = __shfl_up_sync(CS_FULL, incl, o);
+                            if (lane >= (uint32_t)o) incl += up;
+                        }
+                        const uint32_t total = __shfl_sync(CS_FULL, incl, 31);
+                        for (uint32_t q = 0, j = 0; q < cnt; ++q, ++j) {
+                            if (j == skip) ++j;
+                            ttab[incl - cnt + q] = (uint16_t)(lane | (j << 8));
+                        }
+                        __syncwarp();
+                        for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                            const bool has = t0 + lane < total;
+                            const uint32_t te = has ? ttab[t0 + lane] : 0u;
+                            const uint32_t tv = __shfl_sync(CS_FULL, v, te & 31u);
+                            const uint32_t tab = __shfl_sync(CS_FULL, abits, te & 31u);
+                            const uint32_t toff = __shfl_sync(CS_FULL, off, te & 31u);
                             bool improved = false, first = false;
                             uint32_t nb = 0, cbits = 0, back = 0;
                             float cand = 0.f;
-                            if (j < deg && j != skip) {
-                                const CsView V = cs3_view(g, S, v, off, j);
+                            if (has) {
+                                const CsView V = cs3_view(g, S, tv, toff, te >> 8);
                                 cs3_load_block(g, V, cblk, V.sv, V.k + 1);
-                                float a = __uint_as_float(abits);
+                                float a = __uint_as_float(tab);
                                 bool ok = true;
                                 for (uint32_t t = 0; t <= V.k; ++t) {
                                     a = __fadd_rn(a, CS3_CB(V.sv + t));
@@ -406,6 +429,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
                             }
                             relax += improved ? 1ull : 0ull;
                         }
+                        __syncwarp();  // the next batch rewrites the task table
                     }
                     if (R > A.rcap || nn > A.qcap || nf > A.qcap) {
                         fail = R > A.rcap ? CS_ERR_REACH_OVERFLOW : CS_ERR_QUEUE_OVERFLOW;
