@@ -499,10 +499,11 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
     rcap = std::max(rcap, 32u);
     const uint32_t qcap = rcap * 2 + 64;
     uint32_t workers = g->cfg_workers ? g->cfg_workers
-                                      : (uint32_t)g->sm_count * (kind == 3   ? CS3_MIN_BLOCKS * CS3_WARPS
+                                      : (uint32_t)g->sm_count * (kind == 3   ? CS3_WORKERS_PER_SM
                                                                  : kind == 1 ? CS_SEG_MIN_BLOCKS * CS_WARPS_PER_CTA
                                                                              : CS_MIN_BLOCKS * CS_WARPS_PER_CTA);
-    workers = std::max<uint32_t>(CS_WARPS_PER_CTA, workers / CS_WARPS_PER_CTA * CS_WARPS_PER_CTA);
+    const uint32_t gran = kind == 3 ? CS3_WORKERS_PER_SM : CS_WARPS_PER_CTA;  // warps of the widest CTA that uses the arena
+    workers = std::max<uint32_t>(gran, workers / gran * gran);
     CsArenaLayout L{};
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -531,7 +532,7 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
     size_t free_b = 0, total_b = 0;
     CS_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t budget = (size_t)((double)free_b * 0.80);
-    while (workers > CS_WARPS_PER_CTA && (size_t)workers * L.stride > budget) workers -= CS_WARPS_PER_CTA;
+    while (workers > gran && (size_t)workers * L.stride > budget) workers -= gran;
     if ((size_t)workers * L.stride > budget)
         return cs_fail("not enough device memory for the search arena (%zu bytes per worker)", L.stride);
     g->arena_bytes = (size_t)workers * L.stride;
@@ -762,21 +763,24 @@ static float default_delta(const cs_graph* g, float speed) {
 #include "cs_api_v3.inl"
 
 template <int DT>
-static cudaError_t v3_launch_t(const CsShortest3Params& t, uint32_t grid, int threads, cudaStream_t st) {
+static cudaError_t v3_launch_t(const CsShortest3Params& t, uint32_t workers, cudaStream_t st) {
     constexpr uint32_t smem = cs3_smem_bytes<DT>();
+    constexpr uint32_t W = cs3_warps<DT>();
     cudaError_t e = cudaFuncSetAttribute(cs_k_shortest3<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    cs_k_shortest3<DT><<<grid, threads, smem, st>>>(t);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(workers / W, (t.n_sources + W - 1) / W);
+    if (grid == 0) return cudaSuccess;
+    cs_k_shortest3<DT><<<grid, W * 32, smem, st>>>(t);
     return cudaGetLastError();
 }
-static cudaError_t v3_launch(const CsShortest3Params& t, uint32_t grid, int threads, cudaStream_t st) {
+static cudaError_t v3_launch(const CsShortest3Params& t, uint32_t workers, cudaStream_t st) {
     switch (cs_shortest_dt(t.D)) {
-        case 1: return v3_launch_t<1>(t, grid, threads, st);
-        case 2: return v3_launch_t<2>(t, grid, threads, st);
-        case 3: return v3_launch_t<3>(t, grid, threads, st);
-        case 4: return v3_launch_t<4>(t, grid, threads, st);
-        case 8: return v3_launch_t<8>(t, grid, threads, st);
-        default: return v3_launch_t<CS_MAX_THRESHOLDS>(t, grid, threads, st);
+        case 1: return v3_launch_t<1>(t, workers, st);
+        case 2: return v3_launch_t<2>(t, workers, st);
+        case 3: return v3_launch_t<3>(t, workers, st);
+        case 4: return v3_launch_t<4>(t, workers, st);
+        case 8: return v3_launch_t<8>(t, workers, st);
+        default: return v3_launch_t<CS_MAX_THRESHOLDS>(t, workers, st);
     }
 }
 
@@ -953,10 +957,8 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
         t.lay = g->lay;
         t.delta = default_delta(g, speed);
         t.bin_scale = p.bin_scale;
-        const uint32_t grid3 = (uint32_t)std::min<uint64_t>(g->workers / CS3_WARPS, (n_sources + CS3_WARPS - 1) / CS3_WARPS);
         CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
-        const int threads3 = CS3_WARPS * 32;
-        CS_CUDA(v3_launch(t, grid3, threads3, g->stream));
+        CS_CUDA(v3_launch(t, g->workers, g->stream));
         launches += 1;
         CS_CUDA(cudaGetLastError());
         int herr3 = 0;

@@ -16,12 +16,25 @@
 
 #define CS3_KMAX 12       // interiors per chain (longer runs are cut at upload)
 #define CS3_MAX_LINKS 8   // links per junction
+// CTA shape.  The kernel's code (about 125 KB of SASS) is several times the 32 KB instruction cache next to the SM, so
+// every warp of an SM should be in the same phase: up to four thresholds ONE 16-warp CTA per SM moves through the phases
+// in lock step (measured on the 1M-node graph: 2 CTAs x 8 warps 1.22 M sources/s, 1 x 12: 1.25 M, 1 x 14: 1.30 M,
+// 1 x 16: 1.36 M, 1 x 18 at 96 registers: 1.29 M); beyond four thresholds the per-warp shared memory only leaves room
+// for 8-warp CTAs.
+#ifndef CS3_WARPS_WIDE
+#define CS3_WARPS_WIDE 16
+#endif
 #ifndef CS3_WARPS
 #define CS3_WARPS 8
 #endif
 #ifndef CS3_MIN_BLOCKS
 #define CS3_MIN_BLOCKS 2
 #endif
+#define CS3_WORKERS_PER_SM 16  // resident warps per SM of either shape
+template <int DT>
+__host__ __device__ constexpr uint32_t cs3_warps() { return DT <= 4 ? CS3_WARPS_WIDE : CS3_WARPS; }
+template <int DT>
+__host__ __device__ constexpr uint32_t cs3_min_blocks() { return DT <= 4 ? CS3_WORKERS_PER_SM / CS3_WARPS_WIDE : CS3_MIN_BLOCKS; }
 #ifndef CS3_PHASE_SYNC
 #define CS3_PHASE_SYNC 1
 #endif
@@ -218,7 +231,8 @@ __device__ __forceinline__ void cs3_emit_closeness(const CsShortest3Params& p, c
 }
 
 template <int DT>
-__global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3(const CsShortest3Params p) {
+__global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs_k_shortest3(const CsShortest3Params p) {
+    constexpr uint32_t WARPS = cs3_warps<DT>();
     // per-warp shared memory: region A (4 KB): P2 bins | P3 candidates | P4 staged (node, cost) list | P5 node ids / costs;
     // region B (6 KB): P3 walk values | P5 per-node seeds -> credits; region C: P3 / P5 link list, link bytes, P5 outflow
     constexpr uint32_t NB = DT <= 3 ? CS3_NB3 : DT == 4 ? 96u : 24u;  // staged nodes per P5 sub-iteration
@@ -229,13 +243,13 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
     static_assert(BYTES_B >= (CS3_KMAX + 2 + 28) * 32 * 4, "walk values and the chain block must fit region B");
     static_assert(3 * NB * 4 <= BYTES_A && NB >= CS3_KMAX, "P5 node staging must fit region A");
     extern __shared__ __align__(16) uint8_t s_dyn[];
-    __shared__ uint32_t s_hist_all[CS3_WARPS][2][CS_MAX_THRESHOLDS + 1];
-    __shared__ float s_rank_all[CS3_WARPS][CS_MAX_THRESHOLDS];
+    __shared__ uint32_t s_hist_all[WARPS][2][CS_MAX_THRESHOLDS + 1];
+    __shared__ float s_rank_all[WARPS][CS_MAX_THRESHOLDS];
 
     const uint32_t lane = cs_lane();
     const uint32_t ltmask = cs_lanemask_lt();
     const uint32_t wic = threadIdx.x >> 5;
-    const uint32_t worker = blockIdx.x * CS3_WARPS + wic;
+    const uint32_t worker = blockIdx.x * WARPS + wic;
     uint8_t* s_warp = s_dyn + (size_t)wic * BYTES_W;
     uint32_t* bins = reinterpret_cast<uint32_t*>(s_warp);
     uint32_t* l_id = bins;
@@ -272,7 +286,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
     const float one_plus_tol = 1.0f + p.tol;
     const uint32_t INF = CS_INF_BITS;
 
-    // The warps of a CTA take CS3_WARPS consecutive sources and move through the phases together (one barrier per
+    // The warps of a CTA take WARPS consecutive sources and move through the phases together (one barrier per
     // phase): the kernel is far larger than the 32 KB instruction cache level next to the SM, and sixteen warps in
     // sixteen different phases starve on instruction fetch (profiles/r01l: no_instruction was the top stall).
     __shared__ unsigned long long s_base;
@@ -281,7 +295,7 @@ __global__ void __launch_bounds__(CS3_WARPS * 32, CS3_MIN_BLOCKS) cs_k_shortest3
 #if CS3_PHASE_SYNC
         __syncthreads();
         if (threadIdx.x == 0) {
-            s_base = atomicAdd(&p.counters[CS_C_NEXT], (unsigned long long)CS3_WARPS);
+            s_base = atomicAdd(&p.counters[CS_C_NEXT], (unsigned long long)WARPS);
             s_err = *reinterpret_cast<volatile int*>(p.error);
         }
         __syncthreads();
@@ -1263,5 +1277,5 @@ static constexpr uint32_t cs3_smem_bytes() {
     constexpr uint32_t NB = DT <= 3 ? CS3_NB3 : DT == 4 ? 96u : 24u;
     constexpr uint32_t WALK_BYTES = (CS3_KMAX + 2 + 28) * 32 * 4;
     constexpr uint32_t B = 2 * DT * NB * 8 > WALK_BYTES ? 2 * DT * NB * 8 : WALK_BYTES;
-    return CS3_WARPS * (CS_NBINS * 4 + B + 2 * DT * 32 * 8 + 256 * 2 + 256);
+    return cs3_warps<DT>() * (CS_NBINS * 4 + B + 2 * DT * 32 * 8 + 256 * 2 + 256);
 }
