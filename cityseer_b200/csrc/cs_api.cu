@@ -100,6 +100,7 @@ struct cs_graph {
     int opt_kernel = 0;  // 0 auto (chain-contracted kernel when the graph qualifies, else the global-arena kernel),
                          // 1 global-arena kernel, 3 chain-contracted kernel (required)
     float opt_delta_factor = 12.0f;
+    bool seg_optin = false;  // segment kernel: dynamic shared memory opt-in done on this device
     std::vector<uint32_t> in_edge_at;  // container edge id stored at each in-CSR position (tree dumps report edge ids)
 };
 
@@ -500,9 +501,9 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
     const uint32_t qcap = rcap * 2 + 64;
     uint32_t workers = g->cfg_workers ? g->cfg_workers
                                       : (uint32_t)g->sm_count * (kind == 3   ? CS3_WORKERS_PER_SM
-                                                                 : kind == 1 ? CS_SEG_MIN_BLOCKS * CS_WARPS_PER_CTA
+                                                                 : kind == 1 ? CS_SEG_MIN_BLOCKS * CS_SEG_WARPS
                                                                              : CS_MIN_BLOCKS * CS_WARPS_PER_CTA);
-    const uint32_t gran = kind == 3 ? CS3_WORKERS_PER_SM : CS_WARPS_PER_CTA;  // warps of the widest CTA that uses the arena
+    const uint32_t gran = kind == 3 ? CS3_WORKERS_PER_SM : kind == 1 ? CS_SEG_WARPS : CS_WARPS_PER_CTA;  // warps of the widest CTA that uses the arena
     workers = std::max<uint32_t>(gran, workers / gran * gran);
     CsArenaLayout L{};
     size_t off = 0;

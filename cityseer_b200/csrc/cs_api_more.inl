@@ -1,3 +1,17 @@
+// the segment kernel's per-warp bins exceed the 48 KB static limit: opt every instantiation in once per graph (= per device)
+static int segment_smem_optin(cs_graph* g) {
+    if (g->seg_optin) return 0;
+    const int b = (int)CS_SEG_SMEM_BYTES;
+    CS_CUDA(cudaFuncSetAttribute(cs_k_segment<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CS_CUDA(cudaFuncSetAttribute(cs_k_segment<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CS_CUDA(cudaFuncSetAttribute(cs_k_segment<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CS_CUDA(cudaFuncSetAttribute(cs_k_segment<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CS_CUDA(cudaFuncSetAttribute(cs_k_segment<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CS_CUDA(cudaFuncSetAttribute(cs_k_segment<CS_MAX_THRESHOLDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    g->seg_optin = true;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ single-source tree
 // dijkstra_tree_shortest (centrality.rs:1141-1200, :1499-1508): the capped search of the segment kernel (distances by
 // the label-correcting search, exact settle order, single predecessor = the first strict improvement in pop order) run
@@ -10,7 +24,7 @@ extern "C" int cs_dijkstra_tree_shortest(cs_graph* g, uint32_t src, uint32_t max
     if (!(speed_m_s > 0.f) || !std::isfinite(speed_m_s)) return cs_fail("speed_m_s must be finite and positive, got %f", speed_m_s);
     CS_CUDA(cudaSetDevice(g->device));
     g->last_kernel = 0;
-    if (ensure_arena(g, 0, 1)) return 1;
+    if (ensure_arena(g, 1, 1)) return 1;
     uint32_t launches = 0;
     if (stage_sources(g, 1, &src, nullptr, nullptr)) return 1;
     if (prep_seconds(g, speed_m_s, false, &launches)) return 1;
@@ -52,7 +66,8 @@ extern "C" int cs_dijkstra_tree_shortest(cs_graph* g, uint32_t src, uint32_t max
     p.dump_pred = d_pred;
     p.dump_agg = d_agg;
     p.dump_count = d_count;
-    cs_k_segment<1><<<1, CS_WARPS_PER_CTA * 32, 0, g->stream>>>(p);
+    if (segment_smem_optin(g)) return 1;
+    cs_k_segment<1><<<1, CS_SEG_WARPS * 32, CS_SEG_SMEM_BYTES, g->stream>>>(p);
     int rc = 0;
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(g->stream) != cudaSuccess) rc = cs_fail("CUDA error in the tree search");
     int herr = 0;
@@ -121,17 +136,18 @@ extern "C" int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distanc
     p.lay = g->lay;
     p.delta = default_delta(g, speed_m_s);
     p.bin_scale = (float)CS_NBINS / (((float)max_sec + 1.0f) * ((float)max_sec + 1.0f));
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(g->workers / CS_WARPS_PER_CTA,
-                                                       (n_sources + CS_WARPS_PER_CTA - 1) / CS_WARPS_PER_CTA);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(g->workers / CS_SEG_WARPS, (n_sources + CS_SEG_WARPS - 1) / CS_SEG_WARPS);
+    if (segment_smem_optin(g)) return 1;
     CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
     if (grid > 0) {
-        const int threads = CS_WARPS_PER_CTA * 32;
-        if (D == 1) cs_k_segment<1><<<grid, threads, 0, g->stream>>>(p);
-        else if (D == 2) cs_k_segment<2><<<grid, threads, 0, g->stream>>>(p);
-        else if (D == 3) cs_k_segment<3><<<grid, threads, 0, g->stream>>>(p);
-        else if (D == 4) cs_k_segment<4><<<grid, threads, 0, g->stream>>>(p);
-        else if (D <= 8) cs_k_segment<8><<<grid, threads, 0, g->stream>>>(p);
-        else cs_k_segment<CS_MAX_THRESHOLDS><<<grid, threads, 0, g->stream>>>(p);
+        const int threads = CS_SEG_WARPS * 32;
+        const size_t sm = CS_SEG_SMEM_BYTES;
+        if (D == 1) cs_k_segment<1><<<grid, threads, sm, g->stream>>>(p);
+        else if (D == 2) cs_k_segment<2><<<grid, threads, sm, g->stream>>>(p);
+        else if (D == 3) cs_k_segment<3><<<grid, threads, sm, g->stream>>>(p);
+        else if (D == 4) cs_k_segment<4><<<grid, threads, sm, g->stream>>>(p);
+        else if (D <= 8) cs_k_segment<8><<<grid, threads, sm, g->stream>>>(p);
+        else cs_k_segment<CS_MAX_THRESHOLDS><<<grid, threads, sm, g->stream>>>(p);
         launches += 1;
         CS_CUDA(cudaGetLastError());
     }

@@ -53,17 +53,27 @@ __device__ __forceinline__ void cs_seg_terms(float lo, float hi, float hi_imp, f
     bet += (double)b;
 }
 
-// resident CTAs per SM (measured on cfg4: 3 CTAs 795 k sources/s, 4: 788 k, 5: 745 k, 6: 520 k)
-#ifndef CS_SEG_MIN_BLOCKS
-#define CS_SEG_MIN_BLOCKS CS_MIN_BLOCKS
+// CTA shape: ONE CTA per SM whose warps take consecutive sources and move through the phases together (a barrier per
+// phase).  The kernel is about 70 KB of SASS against a 32 KB instruction cache next to the SM; with three independent
+// 8-warp CTAs the warps of an SM sat in different phases and starved on instruction fetch (same finding as the
+// chain-contracted kernel, cs_shortest3.cuh).  Measured on the 1M-node graph (400/800/1600 m): 3 CTAs x 8 warps without
+// barriers 796 k sources/s; one CTA of 16 / 24 / 28 / 32 warps 641 k / 847 k / 887 k / 915 k; 2 x 20 / 2 x 24: 867 k / 799 k.
+#ifndef CS_SEG_WARPS
+#define CS_SEG_WARPS 32
 #endif
+#ifndef CS_SEG_MIN_BLOCKS
+#define CS_SEG_MIN_BLOCKS 1
+#endif
+#define CS_SEG_SMEM_BYTES (CS_SEG_WARPS * CS_NBINS * 4)
 template <int DT>
-__global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_SEG_MIN_BLOCKS) cs_k_segment(const CsSegmentParams p) {
-    __shared__ uint32_t s_bins_all[CS_WARPS_PER_CTA][CS_NBINS];
+__global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_segment(const CsSegmentParams p) {
+    extern __shared__ __align__(16) uint32_t s_bins_all[];  // [CS_SEG_WARPS][CS_NBINS]
+    __shared__ unsigned long long s_base;
+    __shared__ int s_err;
     const uint32_t lane = cs_lane();
     const uint32_t wic = threadIdx.x >> 5;
-    const uint32_t worker = blockIdx.x * CS_WARPS_PER_CTA + wic;
-    uint32_t* bins = s_bins_all[wic];
+    const uint32_t worker = blockIdx.x * CS_SEG_WARPS + wic;
+    uint32_t* bins = s_bins_all + (size_t)wic * CS_NBINS;
     const CsWarpArena A = cs_arena(p.arena, p.lay, worker);
     float2* seglen = reinterpret_cast<float2*>(A.sigma);  // per rank {origin segment length (-1 = pending), last segment length}
     const int D = p.D;
@@ -71,21 +81,31 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_SEG_MIN_BLOCKS) cs_k
     const float f_inf = __uint_as_float(CS_INF_BITS);
 
     for (;;) {
-        unsigned long long si = 0;
-        if (lane == 0) si = atomicAdd(&p.counters[CS_C_NEXT], 1ull);
-        si = __shfl_sync(CS_FULL, si, 0);
-        if (si >= p.n_sources) break;
-        if (*reinterpret_cast<volatile int*>(p.error) != 0) break;
-        const uint32_t src = __ldg(&p.sources[si]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_base = atomicAdd(&p.counters[CS_C_NEXT], (unsigned long long)CS_SEG_WARPS);
+            s_err = *reinterpret_cast<volatile int*>(p.error);
+        }
+        __syncthreads();
+        if (s_base >= p.n_sources || s_err != 0) break;
+        const unsigned long long si = s_base + wic;
+        bool run = si < p.n_sources;  // an idle warp still meets the barriers; its R is 0 and every loop below is empty
+        const uint32_t src = run ? __ldg(&p.sources[si]) : 0u;
 
         unsigned long long relax = 0, edge_iters = 0, n_ci = 0;
-        int fail = 0;
-        const uint32_t R = cs_p1_search(p.g, A, src, p.max_seconds, p.delta, relax, fail);
-        if (fail) {
-            if (lane == 0) atomicCAS(p.error, 0, fail);
-            break;
+        uint32_t R = 0;
+        if (run) {
+            int fail = 0;
+            R = cs_p1_search(p.g, A, src, p.max_seconds, p.delta, relax, fail);
+            if (fail) {
+                if (lane == 0) atomicCAS(p.error, 0, fail);
+                run = false;
+                R = 0;
+            }
         }
-        cs_p2_order(p.g, A, bins, src, R, p.bin_scale, edge_iters);
+        __syncthreads();
+        if (run) cs_p2_order(p.g, A, bins, src, R, p.bin_scale, edge_iters);
+        __syncthreads();
 
         // ------------------------------------------------------------------ S3: tree + closeness, forward
         double dens[DT], harm[DT], bet[DT];
@@ -184,7 +204,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_SEG_MIN_BLOCKS) cs_k
                 if (!__any_sync(CS_FULL, pending)) break;
             }
         }
-        if (p.closeness) {
+        if (run && p.closeness) {
 #pragma unroll
             for (int i = 0; i < DT; ++i) {
                 if (i < D) {
@@ -198,8 +218,9 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_SEG_MIN_BLOCKS) cs_k
             }
         }
 
+        __syncthreads();
         // ------------------------------------------------------------------ S5: subtree sums, reverse settle order
-        if (p.betweenness) {
+        if (run && p.betweenness) {
             for (int b0 = (int)((R - 1) & ~31u); b0 >= 0; b0 -= 32) {
                 const uint32_t r = (uint32_t)b0 + lane;
                 const bool valid = r < R;
@@ -286,6 +307,8 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_SEG_MIN_BLOCKS) cs_k
             }
         }
 
+        __syncthreads();
+        if (!run) continue;
         cs_p6_reset(A, R);
         edge_iters = cs_warp_sum(edge_iters);
         relax = cs_warp_sum(relax);
