@@ -196,3 +196,25 @@ def test_full_size_cfg4_properties_and_kernel_agreement():
     np.testing.assert_allclose(r1._out, ra._out, rtol=1e-9, atol=1e-9)
     for key in ("settled", "edge_iters", "sum_ri", "sum_ci"):
         assert r1.stats[key] == ra.stats[key], key
+
+
+def test_small_worker_counts_round_up_to_whole_ctas():
+    # cs_graph_configure(workers=...) below one CTA of the widest kernel (16 / 32 warps) must still compute everything:
+    # the resident-warp count is rounded up to whole CTAs per kernel, never down to an empty grid
+    ns, _ = synth.config("cfg4", 0.04)
+    full = ns.centrality_shortest(distances=[400, 800], pbar_disabled=True)
+    seg = ns.segment_centrality(distances=[400, 800], pbar_disabled=True)
+    assert full.stats["kernel_used"] == 3
+    ns2, _ = synth.config("cfg4", 0.04)
+    ns2.device_graph().configure(0, 0.0, 8)
+    small = ns2.centrality_shortest(distances=[400, 800], pbar_disabled=True)
+    seg2 = ns2.segment_centrality(distances=[400, 800], pbar_disabled=True)
+    assert small.stats["kernel_used"] == 3 and small.stats["sources"] == full.stats["sources"]
+    assert small.stats["workers"] >= 16
+    assert np.array_equal(small._out[0], full._out[0]) and np.array_equal(small._out[2], full._out[2])
+    np.testing.assert_allclose(small._out, full._out, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(seg2._out, seg._out, rtol=1e-12, atol=1e-9)
+    ns2.device_graph().set_option("kernel", 1)
+    arena = ns2.centrality_shortest(distances=[400, 800], pbar_disabled=True)
+    assert arena.stats["kernel_used"] == 1
+    np.testing.assert_allclose(arena._out, full._out, rtol=RTOL, atol=1e-7)
