@@ -218,3 +218,41 @@ def test_small_worker_counts_round_up_to_whole_ctas():
     arena = ns2.centrality_shortest(distances=[400, 800], pbar_disabled=True)
     assert arena.stats["kernel_used"] == 1
     np.testing.assert_allclose(arena._out, full._out, rtol=RTOL, atol=1e-7)
+
+
+def test_full_size_cfg4_source_sample_vs_oracle(oracle_mod):
+    """BASELINE config #4 at full size against the CPU oracle on a sample of sources the oracle finishes in seconds
+    (its per-source cost is Theta(N), like the reference's): counts bit-exact, floats to rtol 1e-5, device counters
+    equal - for centrality_shortest (chain kernel) and for segment_centrality (configs[3]: 400/800/1600 m)."""
+    ns, _ = synth.config("cfg4")
+    f = ns.frozen()
+    og = oracle_mod.OracleGraph(f)
+    rng = np.random.default_rng(11)
+    src = np.sort(rng.choice(f.node_indices, 160, replace=False)).astype(np.uint32)
+    # centrality_shortest, 500/1000/2000 m
+    dist = [500, 1000, 2000]
+    d, b, s = H.pair(distances=dist)
+    res = ns.centrality_shortest(distances=dist, source_indices=src.tolist(), sample_probability=1.0, pbar_disabled=True)
+    assert res.stats["kernel_used"] == 3
+    elig = np.zeros(f.node_bound, np.uint8)
+    elig[src] = 1
+    ref, cnt = og.centrality_shortest(d, b, s, H.SPEED, sources=src, wt=np.ones(len(src), np.float32), eligible=elig,
+                                      n_threads=8)  # fmt: skip
+    assert np.array_equal(res._out[0], ref[0]) and np.array_equal(res._out[2], ref[2])
+    np.testing.assert_allclose(res._out, ref, rtol=RTOL, atol=1e-7)
+    for key in ("settled", "edge_iters", "sum_ri", "sum_ci"):
+        assert res.stats[key] == cnt[key], key
+    # segment_centrality, 400/800/1600 m, same sources through the C ABI's source list
+    dist = [400, 800, 1600]
+    d, b, s = H.pair(distances=dist)
+    got, st = ns.device_graph().segment_centrality(d, b, s, float(np.float32(H.SPEED)), True, True, src, None, len(src))
+    ref, cnt = og.segment_centrality(d, b, s, H.SPEED, sources=src, n_threads=8)
+    # The exponential terms are differences of two f32 exponentials (centrality.rs:2281-2300, :2380-2391): on a short
+    # segment they cancel, and the last-ulp difference between CUDA's expf and the host's shows up as an absolute
+    # error of a few 1e-6 on elements of order 1e-2 (10 of 12.3 M elements at full size); every other element and the
+    # exp-free rows hold rtol 1e-5.
+    for m, (name, atol) in enumerate((("density", 1e-6), ("harmonic", 1e-6), ("beta", 4e-6), ("betweenness", 4e-6))):
+        np.testing.assert_allclose(got[m], ref[m], rtol=RTOL, atol=atol, err_msg=name)
+        bad = np.abs(got[m] - ref[m]) > RTOL * np.abs(ref[m]) + 1e-6
+        assert bad.sum() <= 32, (name, int(bad.sum()))
+    assert st["settled"] == cnt["settled"] and st["edge_iters"] == cnt["edge_iters"]
