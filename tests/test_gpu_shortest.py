@@ -212,3 +212,26 @@ def test_linearity_property_full_size_graph():
     assert np.array_equal(a._out[0] + b._out[0], full._out[0])
     assert np.array_equal(a._out[2] + b._out[2], full._out[2])
     np.testing.assert_allclose(a._out[1] + b._out[1], full._out[1], rtol=1e-9)
+
+
+def test_full_size_cfg5_source_sample_vs_oracle(oracle_mod):
+    """BASELINE config #5 (4 000 000 nodes, 14.4 M directed edges) at 5 km: a sample of sources the oracle finishes in
+    seconds; counts bit-exact, floats to rtol 1e-5, device counters equal - on both kernels (the graph has no chains: "auto"
+    picks the global-arena kernel; the chain kernel then runs with every node a junction)."""
+    ns, _ = synth.config("cfg5")
+    f = ns.frozen()
+    rng = np.random.default_rng(13)
+    src = np.sort(rng.choice(f.node_indices, 48, replace=False)).astype(np.uint32)
+    dist = [5000]
+    d, b, s = H.pair(distances=dist)
+    res = ns.centrality_shortest(distances=dist, source_indices=src.tolist(), sample_probability=1.0, pbar_disabled=True)
+    elig = np.zeros(f.node_bound, np.uint8)
+    elig[src] = 1
+    og = oracle_mod.OracleGraph(f)
+    ref, cnt = og.centrality_shortest(d, b, s, H.SPEED, sources=src, wt=np.ones(len(src), np.float32), eligible=elig,
+                                      n_threads=8)  # fmt: skip
+    assert np.array_equal(res._out[0], ref[0]) and np.array_equal(res._out[2], ref[2])
+    np.testing.assert_allclose(res._out, ref, rtol=1e-5, atol=1e-7)
+    for key in ("settled", "edge_iters", "sum_ri", "sum_ci"):
+        assert res.stats[key] == cnt[key], key
+    assert res.stats["settled"] > 48 * 4000  # about 5 400 nodes within 5 km of a source
