@@ -235,3 +235,22 @@ def test_full_size_cfg5_source_sample_vs_oracle(oracle_mod):
     for key in ("settled", "edge_iters", "sum_ri", "sum_ci"):
         assert res.stats[key] == cnt[key], key
     assert res.stats["settled"] > 48 * 4000  # about 5 400 nodes within 5 km of a source
+
+
+def test_full_size_cfg2_source_sample_vs_oracle(oracle_mod):
+    """BASELINE config #2 at full size (99 856 nodes), 500/1000/2000 m: a 1500-source sample against the oracle."""
+    ns, _ = synth.config("cfg2")
+    f = ns.frozen()
+    rng = np.random.default_rng(19)
+    src = np.sort(rng.choice(f.node_indices, 1500, replace=False)).astype(np.uint32)
+    dist = [500, 1000, 2000]
+    d, b, s = H.pair(distances=dist)
+    res = ns.centrality_shortest(distances=dist, source_indices=src.tolist(), sample_probability=1.0, pbar_disabled=True)
+    elig = np.zeros(f.node_bound, np.uint8)
+    elig[src] = 1
+    ref, cnt = oracle_mod.OracleGraph(f).centrality_shortest(d, b, s, H.SPEED, sources=src, wt=np.ones(len(src), np.float32),
+                                                             eligible=elig, n_threads=8)  # fmt: skip
+    assert np.array_equal(res._out[0], ref[0]) and np.array_equal(res._out[2], ref[2])
+    np.testing.assert_allclose(res._out, ref, rtol=RTOL, atol=1e-7)
+    for key in ("settled", "edge_iters", "sum_ri", "sum_ci"):
+        assert res.stats[key] == cnt[key], key

@@ -97,3 +97,23 @@ def test_source_subset_and_nonlive(oracle_mod):
     ns.set_node_live(40, False)
     res, ref, _ = run_both(oracle_mod, ns, [800, 2000])
     check(res._out, ref)
+
+
+def test_full_size_cfg3_source_sample_vs_oracle(oracle_mod):
+    """BASELINE config #3 at full size (99 868 dual nodes), 1000/2000 m, wrapper defaults (unit 90, offset 1): a
+    600-source sample against the oracle; density bit-exact, floats to rtol 1e-5, settled-state counts equal."""
+    ns, _ = synth.config("cfg3")
+    f = ns.frozen()
+    rng = np.random.default_rng(17)
+    src = np.sort(rng.choice(f.node_indices, 600, replace=False)).astype(np.uint32)
+    dist = [1000, 2000]
+    d, _b, s = H.pair(distances=dist)
+    res = ns.centrality_simplest(distances=dist, source_indices=src.tolist(), sample_probability=1.0,
+                                 angular_scaling_unit=90.0, farness_scaling_offset=1.0, pbar_disabled=True)  # fmt: skip
+    elig = np.zeros(f.node_bound, np.uint8)
+    elig[src] = 1
+    ref, cnt = oracle_mod.OracleGraph(f).centrality_simplest(
+        d, s, H.SPEED, unit=90.0, offset=1.0, sources=src, wt=np.ones(len(src), np.float32), eligible=elig, n_threads=8)  # fmt: skip
+    check(res._out, ref)
+    assert res.stats["settled"] == cnt["settled"]
+    assert res.stats["settled"] > 600 * 1000
