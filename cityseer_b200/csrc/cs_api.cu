@@ -957,7 +957,7 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
         t.arena = g->d_arena;
         t.lay = g->lay;
         t.delta = default_delta(g, speed);
-        t.bin_scale = p.bin_scale;
+        t.bin_scale = p.bin_scale * ((float)CS3_NBINS / (float)CS_NBINS);
         CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
         CS_CUDA(v3_launch(t, g->workers, g->stream));
         launches += 1;

@@ -38,10 +38,16 @@ __host__ __device__ constexpr uint32_t cs3_min_blocks() { return DT <= 4 ? CS3_W
 #ifndef CS3_PHASE_SYNC
 #define CS3_PHASE_SYNC 1
 #endif
+// Shared memory per warp is kept small on purpose: what the CTA does not take stays L1 cache (16 warps x 12.25 KB left
+// 32 KB of L1; measured on the bench, staging 128 / 112 / 96 / 80 / 64 nodes: 1.35 / 1.42 / 1.41 / 1.36 / 1.29 M sources/s,
+// 112 and 96 share the footprint of the chain-walk scratch).
 #ifndef CS3_NB3
-#define CS3_NB3 128u  // staged nodes per sub-iteration of the dependency pass, up to three thresholds
+#define CS3_NB3 112u  // staged nodes per sub-iteration of the dependency pass, up to three thresholds
 #endif
-#define CS3_LIST 512      // staged (node, cost) entries per warp for the packed closeness scatter
+#ifndef CS3_NBINS
+#define CS3_NBINS 768u  // counting-sort bins of the junction order (the node-level kernels use CS_NBINS = 1024)
+#endif
+#define CS3_LIST 384      // staged (node, cost) entries per warp for the closeness scatter: 32 lanes x CS3_KMAX interiors
 
 struct CsV3Graph {
     uint32_t J, I, n;
@@ -159,6 +165,13 @@ __device__ __forceinline__ void cs3_load_block(const CsV3Graph& g, const CsView&
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+// counting-sort bin of a distance (quadratic in the seconds, so bins fill evenly on a 2-D network); bin_scale is set for
+// CS3_NBINS bins by the host
+__device__ __forceinline__ uint32_t cs3_bin(uint32_t abits, float bin_scale) {
+    const float a = __uint_as_float(abits);
+    return min((uint32_t)(CS3_NBINS - 1), (uint32_t)(__fmul_rn(__fmul_rn(a, a), bin_scale)));
+}
+
 // settle-order tie key of a node (new id): the source first, then ascending original index
 __device__ __forceinline__ uint32_t cs3_key(const CsV3Graph& g, const CsSrc3& S, uint32_t id) {
     return id == S.id ? 0u : __ldg(&g.orig_of_new[id]) + 1u;
@@ -237,11 +250,12 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
     // region B (6 KB): P3 walk values | P5 per-node seeds -> credits; region C: P3 / P5 link list, link bytes, P5 outflow
     constexpr uint32_t NB = DT <= 3 ? CS3_NB3 : DT == 4 ? 96u : 24u;  // staged nodes per P5 sub-iteration
     constexpr uint32_t WALK_BYTES = (CS3_KMAX + 2 + 28) * 32 * 4;
-    constexpr uint32_t BYTES_A = CS_NBINS * 4, BYTES_B = 2 * DT * NB * 8 > WALK_BYTES ? 2 * DT * NB * 8 : WALK_BYTES;
+    constexpr uint32_t BYTES_A = CS3_NBINS * 4, BYTES_B = 2 * DT * NB * 8 > WALK_BYTES ? 2 * DT * NB * 8 : WALK_BYTES;
     constexpr uint32_t BYTES_C = 2 * DT * 32 * 8 + 256 * 2 + 256;
     constexpr uint32_t BYTES_W = BYTES_A + BYTES_B + BYTES_C;
     static_assert(BYTES_B >= (CS3_KMAX + 2 + 28) * 32 * 4, "walk values and the chain block must fit region B");
     static_assert(3 * NB * 4 <= BYTES_A && NB >= CS3_KMAX, "P5 node staging must fit region A");
+    static_assert(CS3_LIST * 8 <= BYTES_A && CS3_LIST >= 32 * CS3_KMAX && CS3_NBINS % 32 == 0, "P4 list must fit region A");
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ uint32_t s_hist_all[WARPS][2][CS_MAX_THRESHOLDS + 1];
     __shared__ float s_rank_all[WARPS][CS_MAX_THRESHOLDS];
@@ -508,18 +522,18 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
             histE[lane] = 0;
         }
         if (run) {
-            for (uint32_t i = lane; i < CS_NBINS; i += 32) bins[i] = 0;
+            for (uint32_t i = lane; i < CS3_NBINS; i += 32) bins[i] = 0;
             __syncwarp();
             for (uint32_t i = lane; i < R; i += 32) {
                 const uint32_t node = cs_ld(&A.node_list[i]);
                 const uint32_t ab = cs_ld(&A.ds[node].x);
                 cs_st(reinterpret_cast<uint32_t*>(&A.s_agg[i]), ab);
-                atomicAdd(&bins[cs_bin(ab, p.bin_scale)], 1u);
+                atomicAdd(&bins[cs3_bin(ab, p.bin_scale)], 1u);
             }
             __syncwarp();
             {
                 uint32_t carry = 0;
-                for (uint32_t k = 0; k < CS_NBINS / 32; ++k) {
+                for (uint32_t k = 0; k < CS3_NBINS / 32; ++k) {
                     const uint32_t c = bins[k * 32 + lane];
                     uint32_t inc = c;
 #pragma unroll
@@ -535,7 +549,7 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
             for (uint32_t i = lane; i < R; i += 32) {
                 const uint32_t node = cs_ld(&A.node_list[i]);
                 const uint32_t ab = cs_ld(reinterpret_cast<const uint32_t*>(&A.s_agg[i]));
-                const uint32_t pos = atomicAdd(&bins[cs_bin(ab, p.bin_scale)], 1u);
+                const uint32_t pos = atomicAdd(&bins[cs3_bin(ab, p.bin_scale)], 1u);
                 const uint32_t key = node == S.slot ? 0u : __ldg(&g.orig_of_new[node]) + 1u;
                 cs_st(&A.tmp_key[pos], ((unsigned long long)ab << 32) | key);
             }
@@ -543,7 +557,7 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
             for (uint32_t pos = lane; pos < R; pos += 32) {
                 const unsigned long long key = cs_ld(&A.tmp_key[pos]);
                 const uint32_t ab = (uint32_t)(key >> 32);
-                const uint32_t bin = cs_bin(ab, p.bin_scale);
+                const uint32_t bin = cs3_bin(ab, p.bin_scale);
                 const uint32_t start = bin ? bins[bin - 1] : 0u;
                 const uint32_t end = bins[bin];
                 uint32_t rank = start;
@@ -1277,5 +1291,5 @@ static constexpr uint32_t cs3_smem_bytes() {
     constexpr uint32_t NB = DT <= 3 ? CS3_NB3 : DT == 4 ? 96u : 24u;
     constexpr uint32_t WALK_BYTES = (CS3_KMAX + 2 + 28) * 32 * 4;
     constexpr uint32_t B = 2 * DT * NB * 8 > WALK_BYTES ? 2 * DT * NB * 8 : WALK_BYTES;
-    return cs3_warps<DT>() * (CS_NBINS * 4 + B + 2 * DT * 32 * 8 + 256 * 2 + 256);
+    return cs3_warps<DT>() * (CS3_NBINS * 4 + B + 2 * DT * 32 * 8 + 256 * 2 + 256);
 }
