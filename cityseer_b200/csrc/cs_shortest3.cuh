@@ -40,12 +40,13 @@ __host__ __device__ constexpr uint32_t cs3_min_blocks() { return DT <= 4 ? CS3_W
 #endif
 // Shared memory per warp is kept small on purpose: what the CTA does not take stays L1 cache (16 warps x 12.25 KB left
 // 32 KB of L1; measured on the bench, staging 128 / 112 / 96 / 80 / 64 nodes: 1.35 / 1.42 / 1.41 / 1.36 / 1.29 M sources/s,
-// 112 and 96 share the footprint of the chain-walk scratch).
+// 112 and 96 share the footprint of the chain-walk scratch).  The shared-memory carve-out comes in steps (.., 164, 196,
+// 228 KB of the SM's 256 KB): 9.5 KB per warp puts the 16-warp CTA under the 164 KB step.
 #ifndef CS3_NB3
 #define CS3_NB3 112u  // staged nodes per sub-iteration of the dependency pass, up to three thresholds
 #endif
 #ifndef CS3_NBINS
-#define CS3_NBINS 768u  // counting-sort bins of the junction order (the node-level kernels use CS_NBINS = 1024)
+#define CS3_NBINS 512u  // counting-sort bins of the junction order (the node-level kernels use CS_NBINS = 1024)
 #endif
 #define CS3_LIST 384      // staged (node, cost) entries per warp for the closeness scatter: 32 lanes x CS3_KMAX interiors
 
@@ -255,7 +256,8 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
     constexpr uint32_t BYTES_W = BYTES_A + BYTES_B + BYTES_C;
     static_assert(BYTES_B >= (CS3_KMAX + 2 + 28) * 32 * 4, "walk values and the chain block must fit region B");
     static_assert(3 * NB * 4 <= BYTES_A && NB >= CS3_KMAX, "P5 node staging must fit region A");
-    static_assert(CS3_LIST * 8 <= BYTES_A && CS3_LIST >= 32 * CS3_KMAX && CS3_NBINS % 32 == 0, "P4 list must fit region A");
+    static_assert(CS3_LIST * 4 <= BYTES_A && CS3_LIST * 4 <= BYTES_B && CS3_LIST >= 32 * CS3_KMAX && CS3_NBINS % 32 == 0,
+                  "P4 list: ids in region A, costs in region B");
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ uint32_t s_hist_all[WARPS][2][CS_MAX_THRESHOLDS + 1];
     __shared__ float s_rank_all[WARPS][CS_MAX_THRESHOLDS];
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
     uint8_t* s_warp = s_dyn + (size_t)wic * BYTES_W;
     uint32_t* bins = reinterpret_cast<uint32_t*>(s_warp);
     uint32_t* l_id = bins;
-    float* l_cost = reinterpret_cast<float*>(bins + CS3_LIST);
+    float* l_cost = reinterpret_cast<float*>(s_warp + BYTES_A);  // P4 only: region B is idle there (no chain walks)
     uint8_t* s_llist2 = reinterpret_cast<uint8_t*>(bins);  // P3: the chunk's links owned by their junction
     uint32_t* s_ids = bins;                        // P5 staged nodes
     float* s_cst = reinterpret_cast<float*>(bins + NB);
