@@ -8,7 +8,9 @@
 #define CS_FULL 0xffffffffu
 #define CS_INF_BITS 0x7f800000u
 #define CS_NOSLOT 0xffffffffu
+#ifndef CS_NBINS
 #define CS_NBINS 1024          // counting-sort bins per source (shared memory, per warp)
+#endif
 #define CS_WARPS_PER_CTA 8
 #define CS_TIE_EPS 1e-4f       // centrality.rs:28
 
