@@ -168,13 +168,55 @@ void reached_nodes(Traversal& t) {
         if (std::isfinite(t.best_route_cost[i])) t.reached_node_indices.push_back(i);
 }
 
-// centrality.rs:1344-1494
-void brandes_shortest(const Graph& g, uint32_t src, uint32_t max_seconds, float speed, float tol, Traversal& t, Counters* c) {
+// Workspace of the "optimised CPU" variant: the SAME arithmetic and visiting order as
+// the faithful restatement, but the Theta(N) per-source allocations of the reference (centrality.rs:1356-1361, :835-836,
+// :1785-1792) are replaced by per-thread arrays that are reset through the list of touched nodes.
+struct SparseWork {
+    Traversal t;
+    std::vector<uint32_t> touched;
+    std::vector<size_t> visit_pos;
+    std::vector<double> seed, seedb, delta, deltab;
+    void ensure(uint32_t n) {
+        if (t.state.size() == n) return;
+        t.state.assign(n, BState());
+        for (uint32_t i = 0; i < n; ++i) t.state[i].node_idx = i;
+        t.best_route_cost.assign(n, F_INF);
+        t.best_agg_seconds.assign(n, F_INF);
+        visit_pos.assign(n, SIZE_MAX);
+        seed.assign(n, 0.0);
+        seedb.assign(n, 0.0);
+        delta.assign(n, 0.0);
+        deltab.assign(n, 0.0);
+    }
+    void reset() {  // back to the state `ensure` leaves, touching only what the last source touched
+        for (uint32_t i : touched) {
+            BState& b = t.state[i];
+            b.visited = false;
+            b.preds.clear();
+            b.sigma = 0.0;
+            b.route_cost = F_INF;
+            b.agg_seconds = F_INF;
+            t.best_route_cost[i] = F_INF;
+            t.best_agg_seconds[i] = F_INF;
+        }
+        touched.clear();
+        t.visited_state_indices.clear();
+        t.reached_node_indices.clear();
+    }
+};
+
+// centrality.rs:1344-1494.  `w` != NULL: sparse-reset variant, `t` is w->t (sized and clean).
+void brandes_shortest(const Graph& g, uint32_t src, uint32_t max_seconds, float speed, float tol, Traversal& t, Counters* c,
+                      SparseWork* w = nullptr) {
     uint32_t n = g.node_bound;
-    t.state.assign(n, BState());
-    for (uint32_t i = 0; i < n; ++i) t.state[i].node_idx = i;
-    t.best_route_cost.assign(n, F_INF);
-    t.best_agg_seconds.assign(n, F_INF);
+    if (!w) {
+        t.state.assign(n, BState());
+        for (uint32_t i = 0; i < n; ++i) t.state[i].node_idx = i;
+        t.best_route_cost.assign(n, F_INF);
+        t.best_agg_seconds.assign(n, F_INF);
+    } else {
+        w->touched.push_back(src);
+    }
     auto& st = t.state;
     st[src].sigma = 1.0;
     st[src].route_cost = 0.0f;
@@ -207,6 +249,7 @@ void brandes_shortest(const Graph& g, uint32_t src, uint32_t max_seconds, float 
             bool improved = cs < st[nb].agg_seconds;
             bool tied = cs <= st[nb].agg_seconds * (1.0f + TIE_EPSILON);
             if (improved) {
+                if (w && st[nb].agg_seconds == F_INF) w->touched.push_back(nb);  // first discovery
                 if (cs < st[nb].agg_seconds * (1.0f - TIE_EPSILON)) {
                     st[nb].preds.clear();
                     st[nb].sigma = st[si].sigma;
@@ -227,7 +270,9 @@ void brandes_shortest(const Graph& g, uint32_t src, uint32_t max_seconds, float 
         }
     }
     if (tol > TIE_EPSILON) {
-        std::vector<size_t> visit_pos(n, SIZE_MAX);
+        std::vector<size_t> visit_pos_own;
+        if (!w) visit_pos_own.assign(n, SIZE_MAX);
+        std::vector<size_t>& visit_pos = w ? w->visit_pos : visit_pos_own;
         for (size_t p = 0; p < t.visited_state_indices.size(); ++p) visit_pos[t.visited_state_indices[p]] = p;
         for (uint32_t idx : t.visited_state_indices) {
             st[idx].preds.clear();
@@ -249,8 +294,16 @@ void brandes_shortest(const Graph& g, uint32_t src, uint32_t max_seconds, float 
                 }
             }
         }
+        if (w)
+            for (uint32_t idx : t.visited_state_indices) visit_pos[idx] = SIZE_MAX;
     }
-    reached_nodes(t);
+    if (!w) {
+        reached_nodes(t);
+    } else {
+        // the reference scans 0..n for finite costs (:1485): the touched nodes in index order are that list
+        t.reached_node_indices = w->touched;
+        std::sort(t.reached_node_indices.begin(), t.reached_node_indices.end());
+    }
     if (c) {
         c->settled += t.visited_state_indices.size();
         c->edge_iters += edge_iters;
@@ -307,8 +360,14 @@ std::vector<uint32_t> sorted_states(const Traversal& t) {
 // centrality.rs:823-873
 template <class FInc, class FCred>
 void backprop(const Traversal& t, const std::vector<uint32_t>& sorted, uint32_t src_node, const std::vector<double>& seed,
-              const std::vector<double>& seed_beta, FInc include, FCred on_credit) {
-    std::vector<double> delta(t.state.size(), 0.0), delta_beta(t.state.size(), 0.0);
+              const std::vector<double>& seed_beta, FInc include, FCred on_credit, SparseWork* w = nullptr) {
+    std::vector<double> delta_own, delta_beta_own;
+    if (!w) {
+        delta_own.assign(t.state.size(), 0.0);
+        delta_beta_own.assign(t.state.size(), 0.0);
+    }
+    std::vector<double>& delta = w ? w->delta : delta_own;  // clean on entry; the caller resets them over `touched`
+    std::vector<double>& delta_beta = w ? w->deltab : delta_beta_own;
     for (uint32_t si : sorted) {
         const BState& s = t.state[si];
         if (!include(s)) continue;
@@ -744,10 +803,11 @@ int orc_betweenness_od(const orc_graph* h, int D, const uint32_t* distances, con
     return 0;
 }
 
-int orc_centrality_shortest(const orc_graph* h, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
-                            float speed, float tol, int closeness, int betweenness, uint64_t n_sources,
-                            const uint32_t* sources, const float* source_wt, const uint8_t* eligible, double* out,
-                            uint64_t* counters_out, uint64_t* reach_totals, int n_threads) {
+static int centrality_shortest_impl(const orc_graph* h, int D, const uint32_t* distances, const float* betas,
+                                    const uint32_t* seconds, float speed, float tol, int closeness, int betweenness,
+                                    uint64_t n_sources, const uint32_t* sources, const float* source_wt,
+                                    const uint8_t* eligible, double* out, uint64_t* counters_out, uint64_t* reach_totals,
+                                    int n_threads, bool sparse) {
     const Graph& g = h->g;
     size_t nb = g.node_bound;
     std::vector<uint32_t> dist(distances, distances + D);
@@ -759,8 +819,12 @@ int orc_centrality_shortest(const orc_graph* h, int D, const uint32_t* distances
     par_for(n_sources, n_threads, [&](uint64_t k) {
         uint32_t src = sources[k];
         float wt = source_wt[k];
-        Traversal t;
-        brandes_shortest(g, src, max_sec, speed, tol, t, &cnt);
+        static thread_local SparseWork tls_work;
+        SparseWork* w = sparse ? &tls_work : nullptr;
+        Traversal t_own;
+        if (w) w->ensure(g.node_bound);
+        Traversal& t = w ? w->t : t_own;
+        brandes_shortest(g, src, max_sec, speed, tol, t, &cnt, w);
         cnt.sources++;
         float cycles_wt = wt / g.weight[src];
         if (closeness) {
@@ -786,13 +850,23 @@ int orc_centrality_shortest(const orc_graph* h, int D, const uint32_t* distances
         }
         if (betweenness) {
             std::vector<uint32_t> sorted = sorted_states(t);
-            std::vector<double> seed(t.state.size()), seedb(t.state.size());
+            std::vector<double> seed_own, seedb_own;
+            if (!w) {
+                seed_own.resize(t.state.size());
+                seedb_own.resize(t.state.size());
+            }
+            std::vector<double>& seed = w ? w->seed : seed_own;
+            std::vector<double>& seedb = w ? w->seedb : seedb_own;
             uint64_t sci = 0;
             for (int i = 0; i < D; ++i) {
                 float thr = (float)dist[i];
                 double beta = (double)betas[i];
-                std::fill(seed.begin(), seed.end(), 0.0);
-                std::fill(seedb.begin(), seedb.end(), 0.0);
+                if (!w) {
+                    std::fill(seed.begin(), seed.end(), 0.0);
+                    std::fill(seedb.begin(), seedb.end(), 0.0);
+                } else {
+                    for (uint32_t q : w->touched) seed[q] = seedb[q] = w->delta[q] = w->deltab[q] = 0.0;
+                }
                 for (uint32_t to : t.reached_node_indices) {
                     if (to == src) continue;
                     if (t.best_route_cost[to] > thr) continue;
@@ -807,10 +881,14 @@ int orc_centrality_shortest(const orc_graph* h, int D, const uint32_t* distances
                         sci++;
                         if (credit > 0.0) atomic_add(M(5, i, node), credit * (double)wt);
                         if (creditb > 0.0) atomic_add(M(6, i, node), creditb * (double)wt);
-                    });
+                    },
+                    w);
             }
+            if (w)
+                for (uint32_t q : w->touched) w->seed[q] = w->seedb[q] = w->delta[q] = w->deltab[q] = 0.0;
             cnt.sum_ci += sci;
         }
+        if (w) w->reset();
     });
     if (counters_out) {
         counters_out[0] = cnt.sources;
@@ -824,6 +902,25 @@ int orc_centrality_shortest(const orc_graph* h, int D, const uint32_t* distances
     if (reach_totals)
         for (int i = 0; i < D; ++i) reach_totals[i] = reach[i];
     return 0;
+}
+
+int orc_centrality_shortest(const orc_graph* h, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
+                            float speed, float tol, int closeness, int betweenness, uint64_t n_sources,
+                            const uint32_t* sources, const float* source_wt, const uint8_t* eligible, double* out,
+                            uint64_t* counters_out, uint64_t* reach_totals, int n_threads) {
+    return centrality_shortest_impl(h, D, distances, betas, seconds, speed, tol, closeness, betweenness, n_sources, sources,
+                                    source_wt, eligible, out, counters_out, reach_totals, n_threads, false);
+}
+
+// "Optimised CPU" variant: identical arithmetic and visiting order, touched-list resets instead of the reference's
+// Theta(N) per-source allocations.  Reported beside the faithful restatement so the GPU is not only compared with the
+// slow formulation; tests/test_oracle_golden.py asserts it equals the faithful port bit for bit.
+int orc_centrality_shortest_opt(const orc_graph* h, int D, const uint32_t* distances, const float* betas,
+                                const uint32_t* seconds, float speed, float tol, int closeness, int betweenness,
+                                uint64_t n_sources, const uint32_t* sources, const float* source_wt, const uint8_t* eligible,
+                                double* out, uint64_t* counters_out, uint64_t* reach_totals, int n_threads) {
+    return centrality_shortest_impl(h, D, distances, betas, seconds, speed, tol, closeness, betweenness, n_sources, sources,
+                                    source_wt, eligible, out, counters_out, reach_totals, n_threads, true);
 }
 
 // out: [4][D][node_bound] = density, farness, harmonic, betweenness.  Returns 1/2 on invalid dual metadata.

@@ -45,6 +45,7 @@ def lib():
         L.orc_graph_destroy.argtypes = [C.c_void_p]
         L.orc_centrality_shortest.argtypes = [C.c_void_p, C.c_int, _u32p, _f32p, _u32p, C.c_float, C.c_float, C.c_int,
                                               C.c_int, C.c_uint64, _u32p, _f32p, _u8p, _f64p, _u64p, _u64p, C.c_int]  # fmt: skip
+        L.orc_centrality_shortest_opt.argtypes = L.orc_centrality_shortest.argtypes
         L.orc_centrality_simplest.argtypes = [C.c_void_p, C.c_int, _u32p, _u32p, C.c_float, C.c_float, C.c_float,
                                               C.c_float, C.c_int, C.c_int, C.c_uint64, _u32p, _f32p, _u8p, _f64p, _u64p,
                                               _u64p, C.c_int]  # fmt: skip
@@ -99,7 +100,8 @@ class OracleGraph:
         return sources, wt, eligible
 
     def centrality_shortest(self, d, b, s, speed, tol=1e-4, closeness=True, betweenness=True, sources=None, wt=None,
-                            eligible=None, n_threads=1):  # fmt: skip
+                            eligible=None, n_threads=1, optimised=False):  # fmt: skip
+        """``optimised=True`` runs the sparse-reset variant (same arithmetic, no Theta(N) work per source)."""
         D = len(d)
         if sources is None:
             sources, wt, eligible = self.default_plan()
@@ -110,7 +112,8 @@ class OracleGraph:
         sources = np.ascontiguousarray(sources, np.uint32)
         wt = np.ascontiguousarray(wt, np.float32)
         eligible = np.ascontiguousarray(eligible, np.uint8)
-        rc = lib().orc_centrality_shortest(self._h, D, _p(da, _u32p), _p(ba, _f32p), _p(sa, _u32p), speed, tol,
+        fn = lib().orc_centrality_shortest_opt if optimised else lib().orc_centrality_shortest
+        rc = fn(self._h, D, _p(da, _u32p), _p(ba, _f32p), _p(sa, _u32p), speed, tol,
                                            int(closeness), int(betweenness), len(sources), _p(sources, _u32p),
                                            _p(wt, _f32p), _p(eligible, _u8p), _p(out, _f64p), _p(cnt, _u64p),
                                            _p(reach, _u64p), n_threads)  # fmt: skip

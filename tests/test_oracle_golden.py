@@ -287,3 +287,34 @@ def test_committed_fixture_matches_the_oracle(oracle_mod):
     fd = nsd.frozen()
     simp, _ = oracle_mod.OracleGraph(fd).centrality_simplest(d, s, H.SPEED, unit=90.0, offset=1.0)
     np.testing.assert_allclose(H.compact(simp, fd), fx["simplest"], rtol=1e-12, atol=0)
+
+
+def test_optimised_cpu_variant_equals_the_faithful_port(oracle_mod):
+    """The sparse-reset "optimised CPU" baseline performs the same arithmetic in the
+    same order as the faithful restatement: single-threaded results and counters are identical bit for bit, with and
+    without the tolerance pass, on mock_graph (exact-run plan) and on a cfg #4 lattice with a non-live border."""
+    from cityseer_b200 import synth
+
+    d, b, s = H.pair(distances=[400, 800, 1600])
+    _g, _n, _e, ns = H.primal_ns()
+    og = oracle_mod.OracleGraph(ns.frozen())
+    for tol in (1e-4, 0.02):
+        ref, c_ref = og.centrality_shortest(d, b, s, H.SPEED, tol=tol)
+        opt, c_opt = og.centrality_shortest(d, b, s, H.SPEED, tol=tol, optimised=True)
+        assert np.array_equal(ref, opt, equal_nan=True) and c_ref == c_opt
+    ns4, _ = synth.config("cfg4", scale=0.08)
+    f = ns4.frozen()
+    og4 = oracle_mod.OracleGraph(f)
+    d, b, s = H.pair(distances=[500, 1000, 2000])
+    rng = np.random.default_rng(3)
+    src = np.sort(rng.choice(f.node_bound, 64, replace=False)).astype(np.uint32)
+    elig = (rng.random(f.node_bound) < 0.8).astype(np.uint8)
+    wt = rng.uniform(0.5, 2.0, len(src)).astype(np.float32)
+    for tol in (1e-4, 0.01):
+        ref, c_ref = og4.centrality_shortest(d, b, s, H.SPEED, tol=tol, sources=src, wt=wt, eligible=elig)
+        opt, c_opt = og4.centrality_shortest(d, b, s, H.SPEED, tol=tol, sources=src, wt=wt, eligible=elig, optimised=True)
+        assert np.array_equal(ref, opt) and c_ref == c_opt
+    # threads only change the order of the f64 atomic adds
+    par, _ = og4.centrality_shortest(d, b, s, H.SPEED, sources=src, wt=wt, eligible=elig, optimised=True, n_threads=4)
+    exact, _ = og4.centrality_shortest(d, b, s, H.SPEED, sources=src, wt=wt, eligible=elig)
+    np.testing.assert_allclose(par, exact, rtol=1e-12, atol=0)
