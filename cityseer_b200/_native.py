@@ -259,8 +259,6 @@ class DeviceGraph:
             "sum_ci": int(st.sum_ci),
             "relaxations": int(st.relaxations),
             "reach_totals": [int(st.reach_totals[i]) for i in range(D)],
-            "dbg15": int(st.reach_totals[15]),
-            "dbg": [int(st.reach_totals[i]) for i in range(10, 15)],
             "kernel_ms": float(st.kernel_ms),
             "total_ms": float(st.total_ms),
             "gpu_launches": int(st.gpu_launches),

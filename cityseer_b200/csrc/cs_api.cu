@@ -63,6 +63,8 @@ struct cs_graph {
     uint64_t sources_cap = 0, n_resident_sources = 0;
     unsigned long long* d_counters = nullptr;
     int* d_error = nullptr;
+    uint32_t* d_redo = nullptr;  // segment: sources set aside for the heap-order replay
+    uint64_t redo_cap = 0;
     double* d_out = nullptr;
     size_t out_cap = 0;
     double* d_acc = nullptr;  // node-interleaved accumulators [n][cw] + [n][bw] (shortest)
@@ -97,6 +99,7 @@ struct cs_graph {
     float* d_od_w = nullptr;
     size_t od_off_cap = 0, od_pairs_cap = 0;
     int last_kernel = 1;
+    int last_herr = 0;   // device error code of the last call (finish_call)
     int opt_kernel = 0;  // 0 auto (chain-contracted kernel when the graph qualifies, else the global-arena kernel),
                          // 1 global-arena kernel, 3 chain-contracted kernel (required)
     float opt_delta_factor = 12.0f;
@@ -228,10 +231,12 @@ extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_ex
             return nullptr;
         }
         if (!std::isnan(seconds[e])) {
-            cs_fail("edge %llu carries explicit seconds (transport edge): outside the centrality hot path", (unsigned long long)e);
-            return nullptr;
-        }
-        if (!(imp_factor[e] > 0.0f) || !std::isfinite(imp_factor[e]) || !std::isfinite(length[e])) {
+            // transport edge (graph.rs:948-985): travel time given, length NaN; edge_travel_seconds returns it as is
+            if (!std::isfinite(seconds[e]) || seconds[e] < 0.0f) {
+                cs_fail("Invalid transport edge payload : seconds must be finite and non-negative (edge %llu)", (unsigned long long)e);
+                return nullptr;
+            }
+        } else if (!(imp_factor[e] > 0.0f) || !std::isfinite(imp_factor[e]) || !std::isfinite(length[e])) {
             cs_fail("Invalid edge payload : imp_factor must be finite and positive (> 0.0) and length finite (edge %llu)",
                     (unsigned long long)e);
             return nullptr;
@@ -326,12 +331,19 @@ extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_ex
     }
     bool twin_missing = false;
     double len_sum = 0.0;
+    uint64_t len_cnt = 0;
     for (uint32_t e : order) {
         const uint32_t s = src[e], d = dst[e];
         const float sp = slope_penalty(z, s, d, length[e]);
-        const float num = (length[e] * imp_factor[e]) * sp;  // use_impedance = true
+        // explicit seconds (transport edges, centrality.rs:988-990) travel through the numerator arrays with the sign
+        // bit set; the prep kernels pass them on undivided
+        const bool fixed_sec = !std::isnan(seconds[e]);
+        const float num = fixed_sec ? -seconds[e] : (length[e] * imp_factor[e]) * sp;  // use_impedance = true
         const bool self_loop = s == d;
-        len_sum += length[e];
+        if (!fixed_sec) {
+            len_sum += length[e];
+            len_cnt += 1;
+        }
         // twin d->s with the same payload edge_idx: first match in d's out-list (graph.rs:1278-1292)
         int64_t twin = -1;
         for (uint32_t k = out_off[d]; k < out_off[d + 1]; ++k) {
@@ -369,7 +381,7 @@ extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_ex
             ar.aux = angle_sum[e];
             float tb = 1e-6f * length[e];  // ANGULAR_ROUTE_TIE_BREAK_FACTOR * length (centrality.rs:667)
             std::memcpy(&ar.meta, &tb, 4);
-            ang_num[out_slot[e]] = (length[e] * 1.0f) * sp;
+            ang_num[out_slot[e]] = fixed_sec ? -seconds[e] : (length[e] * 1.0f) * sp;
         }
     }
     if (is_dual && n >= (1u << 30)) {
@@ -384,7 +396,7 @@ extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_ex
     g->is_dual = is_dual != 0;
     g->dual_status = dual_status;
     g->twin_missing = twin_missing;
-    g->mean_edge_len = E ? (float)(len_sum / (double)E) : 1.0f;
+    g->mean_edge_len = len_cnt ? (float)(len_sum / (double)len_cnt) : 1.0f;
     g->in_edge_at.resize(E);
     for (uint32_t e : order) g->in_edge_at[in_slot[e]] = e;
     cudaDeviceProp prop;
@@ -435,7 +447,7 @@ extern "C" void cs_graph_destroy(cs_graph* g) {
                     (void*)g->d_error, (void*)g->d_out, (void*)g->d_arena, (void*)g->d_acc, (void*)g->d3_jinfo,
                     (void*)g->d3_links, (void*)g->d3_ctab, (void*)g->d3_cnum, (void*)g->d3_csec, (void*)g->d3_weight,
                     (void*)g->d3_int_chain, (void*)g->d3_orig_of_new, (void*)g->d3_new_of_orig, (void*)g->d3_eligible,
-                    (void*)g->d_od_off, (void*)g->d_od_dst, (void*)g->d_od_w})
+                    (void*)g->d_od_off, (void*)g->d_od_dst, (void*)g->d_od_w, (void*)g->d_redo})
         if (p) cudaFree(p);
     if (g->h_progress) cudaFreeHost(g->h_progress);
     for (auto& e : g->ev)
@@ -607,14 +619,18 @@ static int ensure_arena_angular(cs_graph* g, int D) {
     return 0;
 }
 
+// edge_travel_seconds (centrality.rs:988-1006): numerator / speed, or the edge's explicit seconds (sign bit set)
+__device__ __forceinline__ float cs_edge_seconds(float num, float speed) {
+    return (__float_as_uint(num) & 0x80000000u) ? fabsf(num) : __fdiv_rn(num, speed);
+}
 __global__ void cs_k_prep_csec(float* sec, const float* num, size_t m, float speed) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) sec[i] = __fdiv_rn(num[i], speed);
+    if (i < m) sec[i] = cs_edge_seconds(num[i], speed);
 }
 
 __global__ void cs_k_prep_seconds(CsEdge* rec, const float* num, uint64_t E, float speed) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < E) rec[i].sec = __fdiv_rn(num[i], speed);
+    if (i < E) rec[i].sec = cs_edge_seconds(num[i], speed);
 }
 
 static int prep_seconds(cs_graph* g, float speed, bool angular, uint32_t* launches) {
@@ -714,6 +730,7 @@ static int finish_call(cs_graph* g, double* out, int out_on_device, size_t elems
         stats->sum_ri = h[CS_C_SUM_RI];
         stats->sum_ci = h[CS_C_SUM_CI];
         stats->relaxations = h[CS_C_RELAX];
+        stats->fallback_sources = h[CS_C_FALLBACK];
         for (int i = 0; i < CS_MAX_THRESHOLDS; ++i) stats->reach_totals[i] = h[CS_C_REACH0 + i];
         for (int i = 0; i < 8; ++i) stats->phase_cycles[i] = h[CS_C_PHASE0 + i];
         stats->reach_capacity = g->lay.rcap;
@@ -723,6 +740,9 @@ static int finish_call(cs_graph* g, double* out, int out_on_device, size_t elems
         stats->gpu_launches = launches;
         stats->workers = g->workers;
     }
+    g->last_herr = herr;
+    // a warp that stopped on an error left its dense-map entries behind: never reuse the arena as it is
+    if (herr) g->arena_kind = -1;
     if (herr == CS_ERR_REACH_OVERFLOW)
         return cs_fail("search arena overflow: a source reached more than %u nodes; raise reach_capacity via cs_graph_configure",
                        g->lay.rcap);

@@ -66,6 +66,7 @@ extern "C" int cs_dijkstra_tree_shortest(cs_graph* g, uint32_t src, uint32_t max
     p.dump_pred = d_pred;
     p.dump_agg = d_agg;
     p.dump_count = d_count;
+    p.replay = 1;  // one source: always settle equal keys in the reference's heap order
     if (segment_smem_optin(g)) return 1;
     cs_k_segment<1><<<1, CS_SEG_WARPS * 32, CS_SEG_SMEM_BYTES, g->stream>>>(p);
     int rc = 0;
@@ -73,7 +74,10 @@ extern "C" int cs_dijkstra_tree_shortest(cs_graph* g, uint32_t src, uint32_t max
     int herr = 0;
     if (!rc) {
         cudaMemcpy(&herr, g->d_error, sizeof(int), cudaMemcpyDeviceToHost);
-        if (herr) rc = cs_fail("search arena overflow: the source reached more than %u nodes; raise reach_capacity via cs_graph_configure", g->lay.rcap);
+        if (herr) {
+            g->arena_kind = -1;  // the failing warp left its dense-map entries behind
+            rc = cs_fail("search arena overflow: the source reached more than %u nodes; raise reach_capacity via cs_graph_configure", g->lay.rcap);
+        }
     }
     if (!rc) {
         std::vector<uint32_t> hp(n);
@@ -136,10 +140,18 @@ extern "C" int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distanc
     p.lay = g->lay;
     p.delta = default_delta(g, speed_m_s);
     p.bin_scale = (float)CS_NBINS / (((float)max_sec + 1.0f) * ((float)max_sec + 1.0f));
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(g->workers / CS_SEG_WARPS, (n_sources + CS_SEG_WARPS - 1) / CS_SEG_WARPS);
     if (segment_smem_optin(g)) return 1;
-    CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
-    if (grid > 0) {
+    if (g->redo_cap < n_sources) {
+        if (g->d_redo) cudaFree(g->d_redo);
+        g->d_redo = nullptr;
+        g->redo_cap = 0;
+        CS_CUDA(cudaMalloc(&g->d_redo, std::max<uint64_t>(n_sources, 1) * 4));
+        g->redo_cap = n_sources;
+    }
+    p.redo_list = g->d_redo;
+    auto launch = [&](uint64_t m) -> int {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(g->workers / CS_SEG_WARPS, (m + CS_SEG_WARPS - 1) / CS_SEG_WARPS);
+        if (grid == 0) return 0;
         const int threads = CS_SEG_WARPS * 32;
         const size_t sm = CS_SEG_SMEM_BYTES;
         if (D == 1) cs_k_segment<1><<<grid, threads, sm, g->stream>>>(p);
@@ -150,6 +162,26 @@ extern "C" int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distanc
         else cs_k_segment<CS_MAX_THRESHOLDS><<<grid, threads, sm, g->stream>>>(p);
         launches += 1;
         CS_CUDA(cudaGetLastError());
+        return 0;
+    };
+    CS_CUDA(cudaEventRecord(g->ev[1], g->stream));
+    p.replay = 0;
+    if (launch(n_sources)) return 1;
+    // sources where tree parents with bit-equal seconds compete (regular grids, equal pieces) were set aside: serve
+    // them with the heap-order replay (centrality.rs:1589 resolves those ties by BinaryHeap pop order)
+    unsigned long long n_redo = 0;
+    CS_CUDA(cudaMemcpyAsync(&n_redo, g->d_counters + CS_C_FALLBACK, sizeof(n_redo), cudaMemcpyDeviceToHost, g->stream));
+    CS_CUDA(cudaStreamSynchronize(g->stream));
+    if (n_redo) {
+        int herr = 0;
+        CS_CUDA(cudaMemcpy(&herr, g->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+        if (!herr) {
+            CS_CUDA(cudaMemsetAsync(g->d_counters + CS_C_NEXT, 0, sizeof(unsigned long long), g->stream));
+            p.replay = 1;
+            p.sources = g->d_redo;
+            p.n_sources = n_redo;
+            if (launch(n_redo)) return 1;
+        }
     }
     CS_CUDA(cudaEventRecord(g->ev[2], g->stream));
     return finish_call(g, out, out_on_device, elems, d_out, stats, launches);

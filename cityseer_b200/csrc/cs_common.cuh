@@ -63,6 +63,38 @@ __device__ __forceinline__ void cs_red_add(double* p, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 #endif
 }
+// f32 exp as the reference's platform libm computes it.  Rust's f32::exp calls expf; on Linux that is glibc's table-driven
+// algorithm (sysdeps/ieee754/flt-32/e_expf.c, from ARM optimized-routines): exp(x) = 2^(k/32) * 2^(r/32) with a 32-entry
+// table and a cubic in double precision, rounded once to f32.  Restated here because segment_centrality forms DIFFERENCES
+// of two f32 exponentials (centrality.rs:2281-2300, :2380-2391): a last-ulp disagreement in either one is amplified by the
+// cancellation far beyond 1e-5.  The double result carries ~2^-34 relative error before the final rounding, so fused vs
+// unfused multiply-adds on the host cannot change the f32 value (checked against libm: 0 mismatches in 4e5 samples).
+__device__ const unsigned long long cs_exp2f_tab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull, 0x3fef72b83c7d517bull,
+    0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull, 0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull,
+    0x3feedea64c123422ull, 0x3feece086061892dull, 0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull,
+    0x3feea47eb03a5585ull, 0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull, 0x3feee89f995ad3adull,
+    0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull, 0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full,
+    0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+__device__ __forceinline__ float cs_expf_libm(float x) {
+    if (!(x >= -104.0f)) return x != x ? x : 0.0f;  // underflow (and NaN)
+    if (x > 88.72284f) return __uint_as_float(CS_INF_BITS);
+    const double z = 0x1.71547652b82fep+0 * 32.0 * (double)x;
+    const long long ki = __double2ll_rn(z);
+    const double r = z - (double)ki;
+    const unsigned long long t = __ldg(&cs_exp2f_tab[ki & 31]) + ((unsigned long long)ki << 47);
+    const double s = __longlong_as_double((long long)t);
+    const double c0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0, c1 = 0x1.ebfce50fac4f3p-3 / 32.0 / 32.0;
+    const double c2 = 0x1.62e42ff0c52d6p-1 / 32.0;
+    const double zz = c0 * r + c1;
+    const double r2 = r * r;
+    double y = c2 * r + 1.0;
+    y = zz * r2 + y;
+    y = y * s;
+    return (float)y;
+}
+
 __device__ __forceinline__ unsigned long long cs_warp_sum(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CS_FULL, v, o);

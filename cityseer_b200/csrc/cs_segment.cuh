@@ -30,7 +30,126 @@ struct CsSegmentParams {
     uint32_t* dump_pred;   // [n] predecessor node, 0xffffffff = none
     float* dump_agg;       // [n] seconds (prefilled with inf by the caller)
     uint32_t* dump_count;  // [1] number of settled nodes
+    // Equal-key settle order.  The single-predecessor rule (strict `<` in pop order, :1589) makes the tree depend on the
+    // order in which the reference's BinaryHeap pops nodes whose seconds are bit-equal.  replay == 0: a source where two
+    // tree parents with bit-equal seconds compete for a node is not accumulated but appended to redo_list; replay == 1:
+    // the search is replayed by one lane with the Rust heap (cs_seg_replay) and parents are ordered by its pop sequence.
+    int replay;
+    uint32_t* redo_list;
 };
+
+// ---- Rust std::collections::BinaryHeap (max-heap on the reversed f32 order, centrality.rs:358-386) over (rank, seconds
+// bits) items: the first CS_SEG_HEAP_SMEM entries (the levels every sift touches) live in the warp's shared-memory bins,
+// the rest in the arena.  Same sift rules as cs_simplest.cuh's CsHeap (push = sift_up; pop = swap in the last element,
+// sift_down_to_bottom preferring the right child on ties, then sift_up).
+#define CS_SEG_HEAP_SMEM (CS_NBINS / 2)
+struct CsSegHeap {
+    uint2* sm;
+    uint2* gl;
+    uint32_t len;
+    __device__ __forceinline__ uint2 get(uint32_t i) const { return i < CS_SEG_HEAP_SMEM ? sm[i] : cs_ld(&gl[i]); }
+    __device__ __forceinline__ void set(uint32_t i, uint2 v) {
+        if (i < CS_SEG_HEAP_SMEM) sm[i] = v;
+        else cs_st(&gl[i], v);
+    }
+    __device__ __forceinline__ void sift_up(uint32_t pos) {
+        const uint2 hole = get(pos);
+        while (pos > 0) {
+            const uint32_t parent = (pos - 1) / 2;
+            const uint2 pv = get(parent);
+            if (hole.y >= pv.y) break;  // hole <= parent in the reversed order
+            set(pos, pv);
+            pos = parent;
+        }
+        set(pos, hole);
+    }
+    __device__ __forceinline__ void push(uint32_t item, uint32_t bits) {
+        set(len, make_uint2(item, bits));
+        sift_up(len);
+        ++len;
+    }
+    __device__ __forceinline__ uint2 pop() {
+        uint2 item = get(--len);
+        if (len > 0) {
+            const uint2 root = get(0);
+            set(0, item);
+            item = root;
+            const uint32_t end = len;
+            uint32_t pos = 0, child = 1;
+            const uint2 hole = get(0);
+            while (end >= 2 && child <= end - 2) {
+                const uint2 l = get(child), r = get(child + 1);
+                uint2 c = l;
+                if (l.y >= r.y) {  // left <= right: take the right child
+                    child += 1;
+                    c = r;
+                }
+                set(pos, c);
+                pos = child;
+                child = 2 * pos + 1;
+            }
+            if (child == end - 1) {
+                set(pos, get(child));
+                pos = child;
+            }
+            set(pos, hole);
+            sift_up(pos);
+        }
+        return item;
+    }
+};
+
+// Replays dijkstra_tree_segment's heap loop (centrality.rs:1538-1609) over the reached set and records the pop sequence
+// number of every settled node in popseq[rank].  Lane 0 only; the other lanes help with the initialisation.
+__device__ __forceinline__ void cs_seg_replay(const CsGraphDev& g, const CsWarpArena& A, uint32_t* smem_words, uint32_t R,
+                                              float max_seconds, uint32_t* popseq, float* run_agg, int& fail) {
+    const uint32_t lane = cs_lane();
+    for (uint32_t r = lane; r < R; r += 32) {
+        cs_st(&popseq[r], CS_NOSLOT);
+        cs_st(&run_agg[r], __uint_as_float(CS_INF_BITS));
+    }
+    __syncwarp();
+    if (lane == 0) {
+        CsSegHeap h;
+        h.sm = reinterpret_cast<uint2*>(smem_words);
+        h.gl = A.qa;  // qa, qb and far are contiguous and dead after the order pass
+        h.len = 0;
+        const uint32_t cap = 3u * A.qcap;
+        uint32_t seq = 0;
+        cs_st(&run_agg[0], 0.0f);
+        h.push(0u, 0u);
+        while (h.len > 0) {
+            const uint32_t r = h.pop().x;
+            if (cs_ld(&popseq[r]) != CS_NOSLOT) continue;  // lazy deletion (:1545)
+            cs_st(&popseq[r], seq++);
+            const uint32_t cur = cs_ld(&A.s_node[r]);
+            const float base = cs_ld(&run_agg[r]);
+            const uint32_t eb = __ldg(&g.in_off[cur]);
+            const uint32_t e1 = __ldg(&g.in_off[cur + 1]);
+            for (uint32_t e = eb; e < e1; ++e) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&g.in_rec[e]));
+                const uint32_t nb = raw.x;
+                if (nb == cur) continue;
+                const uint2 dnb = cs_ld(&A.ds[nb]);
+                if (dnb.x == CS_INF_BITS) continue;  // every candidate of nb exceeds the cutoff
+                if (cs_ld(&popseq[dnb.y]) != CS_NOSLOT) continue;
+                const float ts = __fadd_rn(base, __uint_as_float(raw.y));
+                if (ts > max_seconds) continue;
+                if (ts < cs_ld(&run_agg[dnb.y])) {
+                    cs_st(&run_agg[dnb.y], ts);
+                    if (h.len >= cap) {
+                        fail = CS_ERR_QUEUE_OVERFLOW;
+                        break;
+                    }
+                    h.push(dnb.y, __float_as_uint(ts));
+                }
+            }
+            if (fail) break;
+        }
+    }
+    fail = __shfl_sync(CS_FULL, fail, 0);
+    __syncwarp();
+}
 
 // one side of a visited edge: integrals of 1, 1/x, exp(-beta x) from `lo` towards `hi_raw`, clipped at the threshold
 __device__ __forceinline__ void cs_seg_terms(float lo, float hi, float hi_imp, float imp, float thr, float beta, double& dens,
@@ -48,7 +167,7 @@ __device__ __forceinline__ void cs_seg_terms(float lo, float hi, float hi_imp, f
         b = __fsub_rn(cur_imp, lo);
     } else {
         const float nb = -beta;
-        b = __fmul_rn(__fsub_rn(expf(__fmul_rn(nb, cur_imp)), expf(__fmul_rn(nb, lo))), __fdiv_rn(1.0f, nb));
+        b = __fmul_rn(__fsub_rn(cs_expf_libm(__fmul_rn(nb, cur_imp)), cs_expf_libm(__fmul_rn(nb, lo))), __fdiv_rn(1.0f, nb));
     }
     bet += (double)b;
 }
@@ -106,6 +225,19 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
         __syncthreads();
         if (run) cs_p2_order(p.g, A, bins, src, R, p.bin_scale, edge_iters);
         __syncthreads();
+        // pop sequence of the reference's heap (replay mode); A.dep is idle until S5
+        uint32_t* popseq = reinterpret_cast<uint32_t*>(A.dep);
+        if (run && p.replay) {
+            int rfail = 0;
+            cs_seg_replay(p.g, A, bins, R, p.max_seconds, popseq, reinterpret_cast<float*>(A.dep) + A.rcap, rfail);
+            if (rfail) {
+                if (lane == 0) atomicCAS(p.error, 0, rfail);
+                cs_p6_reset(A, R);
+                run = false;
+                R = 0;
+            }
+        }
+        bool ambiguous = false;
 
         // ------------------------------------------------------------------ S3: tree + closeness, forward
         double dens[DT], harm[DT], bet[DT];
@@ -122,7 +254,8 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
                 const uint32_t av_bits = __float_as_uint(cs_ld(&A.s_agg[r]));
                 const float av = __uint_as_float(av_bits);
                 // predecessor: earliest-settled u with agg[u] + sec(v->u) == agg[v] exactly (first strict improvement wins)
-                uint32_t best_key = 0xffffffffu, best_pos = 0xffffffffu, best_j = 0;
+                uint32_t best_key = 0xffffffffu, best_pos = 0xffffffffu, best_j = 0, best_rank = CS_NOSLOT;
+                uint32_t best_bits = 0, best_u = 0;
                 if (v != src) {
                     const uint32_t eb = __ldg(&p.g.out_off[v]);
                     const uint32_t deg = __ldg(&p.g.out_off[v + 1]) - eb;
@@ -135,8 +268,14 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
                         const float c = __fadd_rn(__uint_as_float(du.x), __uint_as_float(raw.y));
                         if (__float_as_uint(c) != av_bits) continue;
                         const uint32_t ipos = raw.w & 0xffu;
-                        if (du.y < best_key || (du.y == best_key && ipos < best_pos)) {
-                            best_key = du.y;
+                        // two different parents with bit-equal seconds: the winner is decided by the heap's pop order
+                        if (best_rank != CS_NOSLOT && du.x == best_bits && u != best_u) ambiguous = true;
+                        const uint32_t key = p.replay ? cs_ld(&popseq[du.y]) : du.y;
+                        if (key < best_key || (key == best_key && ipos < best_pos)) {
+                            best_key = key;
+                            best_rank = du.y;
+                            best_bits = du.x;
+                            best_u = u;
                             best_pos = ipos;
                             best_j = j;
                             l_len = __uint_as_float(raw.z);  // length of the twin u->v = the "last segment" of v
@@ -144,10 +283,10 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
                         }
                     }
                 }
-                pred_rank = best_key;
+                pred_rank = best_rank;
                 cs_st(&A.predmask[r], pred_rank == CS_NOSLOT ? 0u : (1u << best_j));
                 if (p.dump_order) {
-                    p.dump_order[r] = v;
+                    p.dump_order[p.replay ? cs_ld(&popseq[r]) : r] = v;
                     p.dump_agg[v] = av;
                     p.dump_pred[v] = pred_rank == CS_NOSLOT ? 0xffffffffu : cs_ld(&A.s_node[pred_rank]);
                     if (r == 0) *p.dump_count = R;
@@ -204,6 +343,13 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
                 if (!__any_sync(CS_FULL, pending)) break;
             }
         }
+        if (run && !p.replay && __any_sync(CS_FULL, ambiguous)) {
+            // leave this source to the replay launch: nothing of it has been accumulated yet
+            if (lane == 0) cs_st(&p.redo_list[atomicAdd(&p.counters[CS_C_FALLBACK], 1ull)], src);
+            cs_p6_reset(A, R);
+            run = false;
+            R = 0;
+        }
         if (run && p.closeness) {
 #pragma unroll
             for (int i = 0; i < DT; ++i) {
@@ -249,9 +395,9 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
                                     auc = __fadd_rn(__fsub_rn(o2s, ms), __fsub_rn(l2s, ms));
                                 } else {
                                     const float nb = -beta, inb = __fdiv_rn(1.0f, nb);
-                                    const float e0 = expf(__fmul_rn(nb, ms));
-                                    auc = __fadd_rn(__fmul_rn(__fsub_rn(expf(__fmul_rn(nb, o2s)), e0), inb),
-                                                    __fmul_rn(__fsub_rn(expf(__fmul_rn(nb, l2s)), e0), inb));
+                                    const float e0 = cs_expf_libm(__fmul_rn(nb, ms));
+                                    auc = __fadd_rn(__fmul_rn(__fsub_rn(cs_expf_libm(__fmul_rn(nb, o2s)), e0), inb),
+                                                    __fmul_rn(__fsub_rn(cs_expf_libm(__fmul_rn(nb, l2s)), e0), inb));
                                 }
                                 if (isfinite(auc) && auc >= 0.0f) own[i] = (double)auc;
                             }

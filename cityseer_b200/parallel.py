@@ -1,13 +1,20 @@
 """Multi-GPU execution of the centrality path: one process per GPU, sources sharded, outputs summed.
 
-The reference has a single data-parallel axis — sources (rayon ``par_iter`` over ``sampling_plan.sources``,
-/root/reference/rust/src/centrality.rs:1703) — with one shared additive ``[M][D][node_bound]`` result.  Here each rank
-owns a contiguous block of the source list and a private device-resident result; one all-reduce (sum, f64) over
-NCCL / NVLink merges them.  All seven arrays need the sum because the reference scatters closeness to the *target*
+The reference has a single data-parallel axis — sources (rayon ``par_iter`` over the source list,
+/root/reference/rust/src/centrality.rs:1703, :1967, :2190) — with one shared additive ``[M][D][node_bound]`` result.
+Here each rank owns a contiguous block of the source list and a private device-resident partial result.  The partials
+are merged with ONE ``reduce_scatter`` (sum, f64) over NCCL / NVLink: rank r ends up with the r-th slice of the summed
+result, downloads only that slice — into a host buffer that all ranks of the node share (POSIX shared memory,
+page-locked by every rank) — and after a barrier every rank reads the complete result from that buffer.  Against an
+all-reduce followed by a full download per rank this moves 1/N of the bytes over each GPU's PCIe link and half the
+bytes over NVLink.  All arrays need the sum because the reference scatters closeness to the *target*
 (centrality.rs:1754-1776); integer-valued metrics stay bit-exact under any summation order (< 2^53).
+
+There is no compute step that consumes the merged data on the device, hence no fused compute+collective kernel.
 """
 from __future__ import annotations
 
+import atexit
 import os
 from collections.abc import Callable
 
@@ -32,18 +39,24 @@ def shard_sources(sources: np.ndarray, wt: np.ndarray, rank: int, world_size: in
     return np.ascontiguousarray(sources[lo:hi]), np.ascontiguousarray(wt[lo:hi])
 
 
+def _dist_state(group=None) -> tuple[int, int]:
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
 def sharded_sum(compute_shard: Callable[[np.ndarray, np.ndarray], "object"], sources: np.ndarray, wt: np.ndarray,
                 group=None):  # fmt: skip
     """Run ``compute_shard(sources_block, wt_block)`` on this rank's block and all-reduce (sum) the returned tensor.
 
     ``compute_shard`` returns a torch tensor (CUDA for the product path, CPU under gloo in tests) holding this rank's
-    partial ``[M][D][node_bound]`` result; the reduced tensor is returned on every rank."""
+    partial ``[M][D][node_bound]`` result; the reduced tensor is returned on every rank.  (The ``*_sharded`` entry
+    points below use the cheaper reduce-scatter merge; this helper is the plain form.)"""
     import torch.distributed as dist
 
-    if dist.is_available() and dist.is_initialized():
-        rank, ws = dist.get_rank(group), dist.get_world_size(group)
-    else:
-        rank, ws = 0, 1
+    rank, ws = _dist_state(group)
     s, w = shard_sources(sources, wt, rank, ws)
     part = compute_shard(s, w)
     if ws > 1:
@@ -51,41 +64,241 @@ def sharded_sum(compute_shard: Callable[[np.ndarray, np.ndarray], "object"], sou
     return part
 
 
-def centrality_shortest_sharded(ns, distances=None, betas=None, minutes=None, compute_closeness=True,
-                                compute_betweenness=True, speed_m_s=None, tolerance=None, group=None):  # fmt: skip
-    """``NetworkStructure.centrality_shortest`` over all ranks of the default process group (exact mode).
+# ---------------------------------------------------------------------------------------------- shared host result
+class _SharedHost:
+    """A host buffer shared by the ranks of one node (``/dev/shm``), page-locked in every rank that has a GPU."""
 
-    Every rank holds the same graph (replicated upload), searches its block of the live sources on its own GPU with a
-    device-resident f64 result, then one NCCL all-reduce sums the blocks.  Returns a ``CentralityShortestResult`` whose
-    arrays are identical on every rank."""
+    def __init__(self, nbytes: int, group, pin: bool):
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+
+        rank, ws = _dist_state(group)
+        self.nbytes = int(nbytes)
+        self._pinned_ptr = None
+        name = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=max(self.nbytes, 8))
+            name[0] = self.shm.name
+        if ws > 1:
+            dist.broadcast_object_list(name, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+            try:  # the creator unlinks; keep this process's resource tracker out of it
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self.shm._name, "shared_memory")  # noqa: SLF001
+            except Exception:  # noqa: BLE001
+                pass
+        self.owner = rank == 0
+        self.array = np.frombuffer(self.shm.buf, dtype=np.uint8, count=self.nbytes)
+        if pin:
+            import torch
+
+            ptr = self.array.ctypes.data
+            err = torch.cuda.cudart().cudaHostRegister(ptr, max(self.nbytes, 8), 0)
+            if int(err) == 0:
+                self._pinned_ptr = ptr
+        if ws > 1:
+            dist.barrier(group=group)
+
+    def close(self):
+        try:
+            if self._pinned_ptr is not None:
+                import torch
+
+                torch.cuda.cudart().cudaHostUnregister(self._pinned_ptr)
+                self._pinned_ptr = None
+            self.array = None
+            self.shm.close()
+            if self.owner:
+                self.shm.unlink()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+_shared_cache: dict[tuple, _SharedHost] = {}
+_partial_cache: dict[tuple, object] = {}
+
+
+@atexit.register
+def _release_shared():
+    for b in _shared_cache.values():
+        b.close()
+    _shared_cache.clear()
+    _partial_cache.clear()
+    _toggle.clear()
+
+
+_toggle: dict[tuple, int] = {}
+
+
+def _shared_host(nbytes: int, group, pin: bool) -> _SharedHost:
+    """Two buffers per size, used alternately: a returned result stays intact through the next merge of the same size
+    (a rank that runs ahead writes into the other buffer)."""
+    base = (int(nbytes), id(group), bool(pin))
+    _toggle[base] = 1 - _toggle.get(base, 1)
+    key = base + (_toggle[base],)
+    if key not in _shared_cache:
+        _shared_cache[key] = _SharedHost(nbytes, group, pin)
+    return _shared_cache[key]
+
+
+def merge_to_host(part, group=None) -> np.ndarray:
+    """Sum the ranks' partial results and return the full result as a host array visible to every rank.
+
+    ``part``: this rank's flat-able torch tensor (same shape on every rank).  NCCL: reduce-scatter, each rank downloads
+    its slice into the node-shared page-locked buffer; gloo (CPU tests): all-reduce, each rank stores its slice.  The
+    returned array is a view of a shared buffer that is reused by the second-next merge of the same size."""
+    import torch
+    import torch.distributed as dist
+
+    rank, ws = _dist_state(group)
+    shape = tuple(part.shape)
+    total = int(part.numel())
+    if ws == 1:
+        if part.is_cuda:
+            from . import _native
+
+            host = _native.pinned_empty(_native.load_library(), shape)  # pooled page-locked buffer
+        else:
+            host = np.empty(shape, np.float64)
+        torch.from_numpy(host).copy_(part)
+        return host
+    chunk = (total + ws - 1) // ws
+    flat = part.reshape(-1)
+    on_gpu = part.is_cuda
+    if on_gpu and dist.get_backend(group) == "nccl":
+        if chunk * ws != total:
+            padded = torch.zeros(chunk * ws, dtype=part.dtype, device=part.device)
+            padded[:total] = flat
+            flat = padded
+        mine = torch.empty(chunk, dtype=part.dtype, device=part.device)
+        dist.reduce_scatter_tensor(mine, flat, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        mine = flat[rank * chunk : min(total, (rank + 1) * chunk)]
+    buf = _shared_host(total * 8, group, pin=on_gpu)
+    host = buf.array.view(np.float64)
+    lo, hi = rank * chunk, min(total, (rank + 1) * chunk)
+    if hi > lo:
+        torch.from_numpy(host[lo:hi]).copy_(mine[: hi - lo])
+    if on_gpu:
+        torch.cuda.current_stream(part.device).synchronize()
+    dist.barrier(group=group)  # every slice is in the shared buffer
+    return host.reshape(shape)
+
+
+def _partial_buffer(shape, device):
+    """This rank's device-resident partial result, reused across calls (the library zeroes it at the start of a call)."""
     import torch
 
+    key = (tuple(shape), str(device))
+    t = _partial_cache.get(key)
+    if t is None:
+        t = torch.empty(shape, dtype=torch.float64, device=device)
+        _partial_cache[key] = t
+    return t
+
+
+def _device_of(dev):
+    import torch
+
+    return torch.device("cuda", dev.device)
+
+
+def _run_on_current_stream(dev, fn):
+    import torch
+
+    dev.set_stream(torch.cuda.current_stream(_device_of(dev)).cuda_stream)
+    try:
+        return fn()
+    finally:
+        dev.set_stream(None)
+
+
+# ---------------------------------------------------------------------------------------------- public entry points
+def centrality_shortest_sharded(ns, distances=None, betas=None, minutes=None, compute_closeness=True,
+                                compute_betweenness=True, min_threshold_wt=None, speed_m_s=None, tolerance=None,
+                                source_indices=None, sample_probability=None, group=None):  # fmt: skip
+    """``NetworkStructure.centrality_shortest`` over all ranks of the process group (centrality.rs:1624-1874).
+
+    Every rank holds the same graph (replicated upload) and searches its block of the sources on its own GPU; the result
+    object is identical on every rank (its arrays view the node-shared host buffer, valid until the next sharded call)."""
     from .rustalgos import WALKING_SPEED, pair_distances_betas_time
     from .rustalgos import centrality as _c
 
     speed = float(WALKING_SPEED if speed_m_s is None else np.float32(speed_m_s))
     tol = _c.validate_tolerance(tolerance)
-    d, b, s = pair_distances_betas_time(speed, distances, betas, minutes)
-    sources, wt, eligible, _n_prog, _tracked, _scale = ns._prepare_sources(None, None, None, None)
+    d, b, s = pair_distances_betas_time(speed, distances, betas, minutes, min_threshold_wt)
+    sources, wt, eligible, _n_prog, tracked, scale = ns._prepare_sources(sample_probability, None, None, source_indices)
+    rank, ws = _dist_state(group)
+    src_block, wt_block = shard_sources(sources, wt, rank, ws)
     dev = ns.device_graph()
-    device = torch.device("cuda", dev.device)
-    stats_box = {}
+    part = _partial_buffer((7, len(d), dev.node_bound), _device_of(dev))
+    _o, st = _run_on_current_stream(dev, lambda: dev.centrality_shortest(
+        d, b, s, speed, tol, compute_closeness, compute_betweenness, src_block, wt_block, eligible, None, len(src_block),
+        out_device_ptr=part.data_ptr()))  # fmt: skip
+    host = merge_to_host(part, group)
+    if compute_betweenness and scale != 1.0:
+        host = host.copy()
+        host[5:7] *= scale
+    res = _c.CentralityShortestResult(d, ns._node_keys_shared(), ns.frozen().node_indices, host, st)
+    if tracked:
+        res.sampled_source_count = int(len(sources))
+    return res
 
-    def compute(src_block, wt_block):
-        out = torch.zeros((7, len(d), dev.node_bound), dtype=torch.float64, device=device)
-        dev.set_stream(torch.cuda.current_stream(device).cuda_stream)
-        try:
-            _o, st = dev.centrality_shortest(d, b, s, speed, tol, compute_closeness, compute_betweenness, src_block,
-                                             wt_block, eligible, None, len(src_block), out_device_ptr=out.data_ptr())  # fmt: skip
-        finally:
-            dev.set_stream(None)
-        stats_box.update(st)
-        return out
 
-    total = sharded_sum(compute, sources, wt, group)
-    # download into a pooled page-locked buffer (full PCIe rate; every rank has its own link)
-    from . import _native
+def centrality_simplest_sharded(ns, distances=None, betas=None, minutes=None, compute_closeness=True,
+                                compute_betweenness=True, min_threshold_wt=None, speed_m_s=None, tolerance=None,
+                                angular_scaling_unit=None, farness_scaling_offset=None, source_indices=None,
+                                sample_probability=None, group=None):  # fmt: skip
+    """``NetworkStructure.centrality_simplest`` (dual graph, centrality.rs:1880-2132) over all ranks."""
+    from .rustalgos import WALKING_SPEED, pair_distances_betas_time
+    from .rustalgos import centrality as _c
 
-    host = _native.pinned_empty(_native.load_library(), tuple(total.shape))
-    torch.from_numpy(host).copy_(total)
-    return _c.CentralityShortestResult(d, ns._node_keys_shared(), ns.frozen().node_indices, host, stats_box)
+    if not ns.is_dual:
+        raise ValueError("centrality_simplest requires a dual graph for angular analysis.")
+    speed = float(WALKING_SPEED if speed_m_s is None else np.float32(speed_m_s))
+    tol = _c.validate_tolerance(tolerance)
+    unit = float(np.float32(180.0 if angular_scaling_unit is None else angular_scaling_unit))
+    offset = float(np.float32(1.0 if farness_scaling_offset is None else farness_scaling_offset))
+    d, _b, s = pair_distances_betas_time(speed, distances, betas, minutes, min_threshold_wt)
+    sources, wt, eligible, _n_prog, tracked, scale = ns._prepare_sources(sample_probability, None, None, source_indices)
+    rank, ws = _dist_state(group)
+    src_block, wt_block = shard_sources(sources, wt, rank, ws)
+    dev = ns.device_graph()
+    part = _partial_buffer((4, len(d), dev.node_bound), _device_of(dev))
+    _o, st = _run_on_current_stream(dev, lambda: dev.centrality_simplest(
+        d, s, speed, tol, unit, offset, compute_closeness, compute_betweenness, src_block, wt_block, eligible, None,
+        len(src_block), out_device_ptr=part.data_ptr()))  # fmt: skip
+    host = merge_to_host(part, group)
+    if compute_betweenness and scale != 1.0:
+        host = host.copy()
+        host[3:4] *= scale
+    res = _c.CentralitySimplestResult(d, ns._node_keys_shared(), ns.frozen().node_indices, host, st)
+    if tracked:
+        res.sampled_source_count = int(len(sources))
+    return res
+
+
+def segment_centrality_sharded(ns, distances=None, betas=None, minutes=None, compute_closeness=True,
+                               compute_betweenness=True, min_threshold_wt=None, speed_m_s=None, group=None):  # fmt: skip
+    """``NetworkStructure.segment_centrality`` (centrality.rs:2134-2407) over all ranks: the live nodes are the sources
+    (:2194); closeness lands at the source, betweenness at the tree ancestors, both merged by the same sum."""
+    from .rustalgos import WALKING_SPEED, pair_distances_betas_time
+    from .rustalgos import centrality as _c
+
+    speed = float(WALKING_SPEED if speed_m_s is None else np.float32(speed_m_s))
+    d, b, s = pair_distances_betas_time(speed, distances, betas, minutes, min_threshold_wt)
+    f = ns.frozen()
+    live = f.live[f.node_indices].astype(bool)
+    sources = np.ascontiguousarray(f.node_indices[live], dtype=np.uint32)
+    rank, ws = _dist_state(group)
+    lo, hi = shard_bounds(len(sources), rank, ws)
+    dev = ns.device_graph()
+    part = _partial_buffer((4, len(d), dev.node_bound), _device_of(dev))
+    _o, st = _run_on_current_stream(dev, lambda: dev.segment_centrality(
+        d, b, s, speed, compute_closeness, compute_betweenness, np.ascontiguousarray(sources[lo:hi]), None, hi - lo,
+        out_device_ptr=part.data_ptr()))  # fmt: skip
+    host = merge_to_host(part, group)
+    return _c.CentralitySegmentResult(d, ns._node_keys_shared(), f.node_indices, host, st)

@@ -11,6 +11,7 @@ from __future__ import annotations
 import math
 import re
 import threading
+from array import array
 from typing import Any
 
 import numpy as np
@@ -80,7 +81,7 @@ class NodePayload:
 
 
 class EdgePayload:
-    """graph.rs:89-115 (street edges)."""
+    """graph.rs:89-115 (street edges, and transport edges defined by their travel time)."""
 
     __slots__ = (
         "start_nd_key_py", "end_nd_key_py", "shared_primal_node_key", "edge_idx", "length", "angle_sum", "imp_factor",
@@ -93,6 +94,14 @@ class EdgePayload:
                 f"Invalid edge payload : imp_factor must be finite and positive (> 0.0). Found {self.imp_factor}. "
                 f"Start key: {self.start_nd_key_py!r}, End key: {self.end_nd_key_py!r}"
             )
+        if getattr(self, "is_transport", False) and not math.isnan(self.seconds):
+            # graph.rs:152-160
+            if not math.isfinite(self.seconds) or self.seconds < 0.0:
+                raise ValueError(
+                    "Invalid transport edge payload : seconds must be finite and non-negative. "
+                    f"Start key: {self.start_nd_key_py!r}, End key: {self.end_nd_key_py!r}"
+                )
+            return
         if not math.isfinite(self.length):
             raise ValueError(f"Invalid street edge payload : length must be finite. Found {self.length}.")
         if not math.isfinite(self.angle_sum):
@@ -193,6 +202,12 @@ class NetworkStructure:
         self._out: list[list[int]] = []  # per node: edge ids, oldest first (iterate reversed = petgraph order)
         self._in: list[list[int]] = []
         self._stamp = 0
+        # columnar mirror of the payload fields the kernels read, maintained at mutation time: frozen() is a handful of
+        # list -> ndarray conversions instead of a Python loop over every node and edge
+        self._ncol = {k: array(t) for k, t in (("x", "d"), ("y", "d"), ("z", "d"), ("live", "B"), ("weight", "f"), ("exists", "B"))}
+        self._ecol = {k: array(t) for k, t in (("src", "I"), ("dst", "I"), ("edge_idx", "I"), ("length", "f"), ("angle_sum", "f"),
+                                               ("imp", "f"), ("seconds", "f"), ("stamp", "Q"), ("key", "i"), ("exists", "B"))}  # fmt: skip
+        self._key_ids: dict[str, int] = {}
         self._is_dual = False
         self._progress = _native.ProgressCounter()
         self._frozen: FrozenGraph | None = None
@@ -233,21 +248,59 @@ class NetworkStructure:
                               float(np.float32(weight)))  # fmt: skip
         payload.validate()
         self._invalidate()
+        return self._add_node_internal(payload)
+
+    def _add_node_internal(self, payload: NodePayload) -> int:
+        c = self._ncol
+        row = (payload.x, payload.y, math.nan if payload.z is None else payload.z, 1 if payload.live else 0,
+               payload.weight, 1)  # fmt: skip
         if self._free_nodes:
             idx = self._free_nodes.pop()
             self._nodes[idx] = payload
+            for k, v in zip(("x", "y", "z", "live", "weight", "exists"), row):
+                c[k][idx] = v
         else:
             idx = len(self._nodes)
             self._nodes.append(payload)
             self._out.append([])
             self._in.append([])
+            for k, v in zip(("x", "y", "z", "live", "weight", "exists"), row):
+                c[k].append(v)
         return idx
 
     def add_transport_node(self, *args, **kwargs):
-        raise NotImplementedError("transport nodes are outside the centrality hot path (SURVEY.md §8f-4)")
+        """graph.rs:455-555 links the new node to nearby street nodes through the edge R-tree and the data-assignment
+        search (graph.rs:1064-1232), which is outside this build's scope (land-use assignment).  Add the
+        stop with ``add_street_node(..., live=False, weight=0)`` and connect it with ``add_transport_edge`` instead."""
+        raise NotImplementedError(
+            "add_transport_node needs the edge R-tree / data-assignment search (out of scope); add the stop as a "
+            "non-live street node and connect it with add_transport_edge"
+        )
 
-    def add_transport_edge(self, *args, **kwargs):
-        raise NotImplementedError("transport edges are outside the centrality hot path (SURVEY.md §8f-4)")
+    def add_transport_edge(self, start_nd_idx: int, end_nd_idx: int, edge_idx: int, start_nd_key_py, end_nd_key_py,
+                           seconds: float, imp_factor: float | None = None) -> int:  # fmt: skip
+        """graph.rs:946-985 — an abstract edge defined by its travel time: ``seconds`` is what
+        ``edge_travel_seconds`` returns for it at any speed (centrality.rs:988-990); length / angle are NaN."""
+        sec = float(np.float32(seconds))
+        if not math.isfinite(sec) or sec < 0.0:
+            raise ValueError(
+                f"Invalid seconds value ({seconds}) for transport edge (idx {edge_idx}) between nodes {start_nd_idx} "
+                f"and {end_nd_idx}."
+            )
+        p = EdgePayload()
+        p.start_nd_key_py = start_nd_key_py
+        p.end_nd_key_py = end_nd_key_py
+        p.shared_primal_node_key = None
+        p.edge_idx = int(edge_idx)
+        p.length = math.nan
+        p.angle_sum = math.nan
+        p.imp_factor = 1.0 if imp_factor is None else float(np.float32(imp_factor))
+        p.in_bearing = math.nan
+        p.out_bearing = math.nan
+        p.seconds = sec
+        p.geom_wkt = None
+        p.is_transport = True
+        return self._add_edge_internal(start_nd_idx, end_nd_idx, p)
 
     def _require_node(self, node_idx: int, param: str) -> NodePayload:
         # graph.rs:1248-1258
@@ -282,6 +335,7 @@ class NetworkStructure:
         if node_idx < 0 or node_idx >= len(self._nodes) or self._nodes[node_idx] is None:
             raise ValueError(f"Node index {node_idx} does not exist in the graph.")
         self._nodes[node_idx].live = bool(live)  # type: ignore[union-attr]
+        self._ncol["live"][node_idx] = 1 if live else 0
         self._invalidate()
 
     def remove_street_node(self, node_idx: int) -> None:
@@ -293,6 +347,8 @@ class NetworkStructure:
             while lst[node_idx]:
                 self._remove_edge_id(lst[node_idx][-1])
         self._nodes[node_idx] = None
+        self._ncol["exists"][node_idx] = 0
+        self._ncol["live"][node_idx] = 0
         self._free_nodes.append(node_idx)
 
     def node_count(self) -> int:
@@ -430,12 +486,22 @@ class NetworkStructure:
         p._dst = end_nd_idx
         self._stamp += 1
         p._stamp = self._stamp
+        key = -1
+        if p.shared_primal_node_key is not None:
+            key = self._key_ids.setdefault(p.shared_primal_node_key, len(self._key_ids))
+        row = (start_nd_idx, end_nd_idx, p.edge_idx, p.length, p.angle_sum, p.imp_factor, p.seconds, p._stamp, key, 1)
+        names = ("src", "dst", "edge_idx", "length", "angle_sum", "imp", "seconds", "stamp", "key", "exists")
+        c = self._ecol
         if self._free_edges:
             eid = self._free_edges.pop()
             self._edges[eid] = p
+            for k, v in zip(names, row):
+                c[k][eid] = v
         else:
             eid = len(self._edges)
             self._edges.append(p)
+            for k, v in zip(names, row):
+                c[k].append(v)
         self._out[start_nd_idx].append(eid)
         self._in[end_nd_idx].append(eid)
         return eid
@@ -445,6 +511,7 @@ class NetworkStructure:
         self._out[p._src].remove(eid)
         self._in[p._dst].remove(eid)
         self._edges[eid] = None
+        self._ecol["exists"][eid] = 0
         self._free_edges.append(eid)
 
     def _find_edge(self, start_nd_idx: int, end_nd_idx: int, edge_idx: int) -> int | None:
@@ -578,51 +645,41 @@ class NetworkStructure:
         f = FrozenGraph()
         nb = self.node_bound()
         eb = self.edge_bound()
+        def col(c, name, m, dtype):
+            return np.frombuffer(c[name], dtype=dtype)[:m].copy() if m else np.zeros(0, dtype)
+
+        nc, ec = self._ncol, self._ecol
         f.node_bound = nb
-        f.node_exists = np.zeros(nb, np.uint8)
-        f.live = np.zeros(nb, np.uint8)
-        f.weight = np.zeros(nb, np.float32)
-        f.z = np.full(nb, np.nan, np.float64)
-        f.xs = np.zeros(nb, np.float64)
-        f.ys = np.zeros(nb, np.float64)
-        for i in range(nb):
-            p = self._nodes[i]
-            if p is None:
-                continue
-            f.xs[i] = p.x
-            f.ys[i] = p.y
-            f.node_exists[i] = 1
-            f.live[i] = 1 if p.live else 0
-            f.weight[i] = p.weight
-            if p.z is not None:
-                f.z[i] = p.z
+        f.node_exists = col(nc, "exists", nb, np.uint8)
+        gone = f.node_exists == 0
+        f.live = col(nc, "live", nb, np.uint8)
+        f.weight = col(nc, "weight", nb, np.float32)
+        f.z = col(nc, "z", nb, np.float64)
+        f.xs = col(nc, "x", nb, np.float64)
+        f.ys = col(nc, "y", nb, np.float64)
+        if gone.any():  # removed nodes read as the defaults
+            f.live[gone] = 0
+            f.weight[gone] = 0
+            f.z[gone] = np.nan
+            f.xs[gone] = 0
+            f.ys[gone] = 0
         f.edge_bound = eb
-        f.edge_exists = np.zeros(eb, np.uint8)
-        f.src = np.zeros(eb, np.uint32)
-        f.dst = np.zeros(eb, np.uint32)
-        f.edge_idx = np.zeros(eb, np.uint32)
-        f.length = np.zeros(eb, np.float32)
-        f.angle_sum = np.zeros(eb, np.float32)
-        f.imp = np.ones(eb, np.float32)
-        f.seconds = np.full(eb, np.nan, np.float32)
-        f.shared_key = np.full(eb, -1, np.int32)
-        f.stamp = np.zeros(eb, np.uint64)
-        key_ids: dict[str, int] = {}
-        for i in range(eb):
-            e = self._edges[i]
-            if e is None:
-                continue
-            f.edge_exists[i] = 1
-            f.src[i] = e._src
-            f.dst[i] = e._dst
-            f.edge_idx[i] = e.edge_idx
-            f.length[i] = e.length
-            f.angle_sum[i] = e.angle_sum
-            f.imp[i] = e.imp_factor
-            f.seconds[i] = e.seconds
-            f.stamp[i] = e._stamp
-            if e.shared_primal_node_key is not None:
-                f.shared_key[i] = key_ids.setdefault(e.shared_primal_node_key, len(key_ids))
+        f.edge_exists = col(ec, "exists", eb, np.uint8)
+        egone = f.edge_exists == 0
+        f.src = col(ec, "src", eb, np.uint32)
+        f.dst = col(ec, "dst", eb, np.uint32)
+        f.edge_idx = col(ec, "edge_idx", eb, np.uint32)
+        f.length = col(ec, "length", eb, np.float32)
+        f.angle_sum = col(ec, "angle_sum", eb, np.float32)
+        f.imp = col(ec, "imp", eb, np.float32)
+        f.seconds = col(ec, "seconds", eb, np.float32)
+        f.shared_key = col(ec, "key", eb, np.int32)
+        f.stamp = col(ec, "stamp", eb, np.uint64)
+        if egone.any():
+            for a, v in ((f.src, 0), (f.dst, 0), (f.edge_idx, 0), (f.length, 0), (f.angle_sum, 0), (f.imp, 1),
+                         (f.seconds, np.nan), (f.shared_key, -1), (f.stamp, 0)):  # fmt: skip
+                a[egone] = v
+        key_ids = dict(self._key_ids)
         f.is_dual = self._is_dual
         f.node_indices = np.nonzero(f.node_exists)[0].astype(np.int64)
         f.key_names = key_ids

@@ -68,7 +68,15 @@ def _directed_in_ingest_order(n: int, edges: np.ndarray):
     return src[order], dst[order]
 
 
-def primal_network(xy: np.ndarray, edges: np.ndarray, live: np.ndarray | None = None) -> NetworkStructure:
+def terrain(xy: np.ndarray, relief: float = 30.0) -> np.ndarray:
+    """Smooth synthetic elevation (metres) over the lattice: gradients of a few percent, so the Tobler slope penalty
+    (centrality.rs:969-984) makes the two directions of every edge differ."""
+    x, y = xy[:, 0] - X0, xy[:, 1] - Y0
+    return relief * np.sin(x / 700.0) * np.cos(y / 500.0) + 0.004 * x - 0.002 * y
+
+
+def primal_network(xy: np.ndarray, edges: np.ndarray, live: np.ndarray | None = None,
+                   z: np.ndarray | None = None) -> NetworkStructure:  # fmt: skip
     n = len(xy)
     src, dst = _directed_in_ingest_order(n, edges)
     d = xy[dst] - xy[src]
@@ -80,6 +88,7 @@ def primal_network(xy: np.ndarray, edges: np.ndarray, live: np.ndarray | None = 
         dst=dst,
         edge_idx=np.zeros(len(src), np.uint32),
         length=length,
+        z=z,
         x=xy[:, 0],
         y=xy[:, 1],
     )
@@ -92,7 +101,7 @@ def _turn_angle(a: np.ndarray, b: np.ndarray, c: np.ndarray) -> np.ndarray:
     return np.abs(np.mod(a2 - a1 + 180.0, 360.0) - 180.0)
 
 
-def dual_network(xy: np.ndarray, edges: np.ndarray) -> NetworkStructure:
+def dual_network(xy: np.ndarray, edges: np.ndarray, z: np.ndarray | None = None) -> NetworkStructure:
     """Dual of a straight-edged primal graph (graphs.py:2077-2147): dual node per primal edge at its midpoint, dual edge
     per pair of primal edges sharing a node with geometry [mid_a, shared, mid_b]."""
     m = len(edges)
@@ -135,26 +144,28 @@ def dual_network(xy: np.ndarray, edges: np.ndarray) -> NetworkStructure:
         angle_sum=angle,
         shared_key=sh.astype(np.int32),
         is_dual=True,
+        z=None if z is None else (z[edges[:, 0]] + z[edges[:, 1]]) / 2.0,
         x=mid[:, 0],
         y=mid[:, 1],
     )
 
 
-def config(name: str, scale: float = 1.0):
-    """Named BASELINE.json workloads → (NetworkStructure, description dict).  ``scale`` < 1 shrinks the lattice side."""
+def config(name: str, scale: float = 1.0, hilly: bool = False):
+    """Named BASELINE.json workloads → (NetworkStructure, description dict).  ``scale`` < 1 shrinks the lattice side;
+    ``hilly`` gives every node an elevation (slope-penalised, direction-dependent edge seconds)."""
     if name == "cfg2":  # 100k-node perturbed grid, primal
         side = max(8, int(316 * scale))
         xy, e = lattice(side, side, seed=42)
-        return primal_network(xy, e), {"workload": "cfg2-100k-primal-grid", "lattice": side}
+        return primal_network(xy, e, z=terrain(xy) if hilly else None), {"workload": "cfg2-100k-primal-grid", "lattice": side}
     if name == "cfg3":  # 100k-node dual
         side = max(8, int(236 * scale))
         xy, e = lattice(side, side, seed=42)
-        return dual_network(xy, e), {"workload": "cfg3-100k-dual", "lattice": side}
+        return dual_network(xy, e, z=terrain(xy) if hilly else None), {"workload": "cfg3-100k-dual", "lattice": side}
     if name == "cfg4":  # 1M-node decomposed (20 m segments)
         side = max(8, int(333 * scale))
         xy, e = lattice(side, side, seed=42)
         xy2, e2 = decompose(xy, e, 20.0)
-        return primal_network(xy2, e2), {"workload": "cfg4-1M-decomposed-20m", "lattice": side}
+        return primal_network(xy2, e2, z=terrain(xy2) if hilly else None), {"workload": "cfg4-1M-decomposed-20m", "lattice": side}
     if name == "cfg5":  # 4M-node metro
         side = max(8, int(2000 * scale))
         xy, e = lattice(side, side, seed=42)

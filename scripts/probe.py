@@ -61,7 +61,7 @@ for rep in range(a.reps):
                       "fallback": s["fallback_sources"],
                       "phase_pct": [round(100.0 * c / max(1, sum(s["phase_cycles"][:6])), 1) for c in s["phase_cycles"][:6]],
                       "cycles_per_source": sum(s["phase_cycles"][:5]) / max(1, s["sources"]),
-                      "init_kcyc": round(s["dbg15"] / max(1, s["sources"]) / 1e3, 1), "dbg_kcyc": [round(c / max(1, s["sources"]) / 1e3, 1) for c in s["dbg"]], "phase_kcyc": [round(c / max(1, s["sources"]) / 1e3, 1) for c in s["phase_cycles"][:6]],
+                      "phase_kcyc": [round(c / max(1, s["sources"]) / 1e3, 1) for c in s["phase_cycles"][:6]],
                       "p1_iters": s["phase_cycles"][6] / max(1, s["sources"]), "p1_splits": s["phase_cycles"][7] / max(1, s["sources"]),
                       "kernel_used": s["kernel_used"], "smem": s["smem_bytes"], "ctas_per_sm": s["ctas_per_sm"], "rcap": s["reach_capacity"],
                       "slots": s["slot_capacity"]}), flush=True)

@@ -1,5 +1,7 @@
-"""Multi-rank path on CPU: two gloo ranks shard the sources, each computes its block (with the CPU oracle standing in for
-the device call), one all-reduce sums the partial results — equal to the single-rank result."""
+"""Multi-rank HOST logic on CPU (no device path here: the GPU side of the sharded calls is covered by the `-m gpu` test
+that runs scripts/check_sharded.py under torchrun).  Two gloo ranks shard the sources, each computes its block with the
+CPU oracle standing in for the device call, and the partial results are merged (a) by the plain all-reduce helper and
+(b) by ``merge_to_host`` — slices assembled in the node-shared host buffer — both equal to the single-rank result."""
 import os
 import socket
 
@@ -38,6 +40,13 @@ def _worker(rank, world, port, q):
 
     total = parallel.sharded_sum(compute, sources, wt)
     lo, hi = parallel.shard_bounds(len(sources), rank, world)
+    # the product merge: every rank's slice of the sum lands in one host buffer shared by the ranks of the node
+    merged = []
+    for _rep in range(3):  # alternating buffers: three merges in a row stay consistent
+        part = compute(*parallel.shard_sources(sources, wt, rank, world))
+        merged.append(parallel.merge_to_host(part).copy())
+    assert all(np.array_equal(m, merged[0]) for m in merged)
+    assert np.array_equal(merged[0], total.numpy())
     q.put((rank, total.numpy(), (lo, hi)))
     dist.barrier()
     dist.destroy_process_group()
