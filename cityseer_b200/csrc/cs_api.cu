@@ -538,6 +538,7 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
     if (kind == 3) {
         L.frank = take((size_t)rcap * CS3_MAX_LINKS * 16);  // chain kernel: per link {candidate, neighbour, id, far rank}
         L.needm = take((size_t)rcap * 4);                  // chain kernel: links whose far junction continues the path
+        L.jrank = take((size_t)rcap * 8);                  // chain kernel: junction record by settle rank
     }
     L.stride = align_up(off, 4096);
     L.rcap = rcap;

@@ -250,8 +250,8 @@ static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, c
                 orig_of_new[next++] = v;
             }
     }
-    // ---- seconds numerators: per chain fwd[0..k] (wave A -> B, step t uses the edge m_{t+1} -> m_t) then
-    //      bwdr[0..k] (wave B -> A, step t uses the edge m_{k-t} -> m_{k+1-t})
+    // ---- seconds numerators: per chain fwd[0..k] (wave A -> B, step t uses the edge m_{t+1} -> m_t), padding to a
+    //      multiple of four floats, then bwdr[0..k] (wave B -> A, step t uses the edge m_{k-t} -> m_{k+1-t})
     const uint32_t C = NC + (uint32_t)directs.size();
     std::vector<uint32_t> soff(C, 0);
     std::vector<float> cnum;
@@ -279,13 +279,15 @@ static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, c
             }
         }
         for (uint32_t t = 0; t <= k; ++t) cnum.push_back(fwd[t]);
+        while (cnum.size() & 3u) cnum.push_back(0.f);  // bwdr starts at cs3_pb(k): both arrays 16-byte aligned
         for (uint32_t t = 0; t <= k; ++t) cnum.push_back(bwd[k - t]);
     }
     for (uint32_t d = 0; d < directs.size(); ++d) {
         while (cnum.size() & 3u) cnum.push_back(0.f);
         soff[NC + d] = (uint32_t)cnum.size();
         cnum.push_back(in_num[directs[d].slotA]);  // B -> A: A's outward step
-        cnum.push_back(in_num[directs[d].slotB]);  // A -> B: B's outward step
+        while (cnum.size() & 3u) cnum.push_back(0.f);
+        cnum.push_back(in_num[directs[d].slotB]);  // A -> B: B's outward step (at cs3_pb(0))
     }
     while (cnum.size() & 3u) cnum.push_back(0.f);
     // ---- link records by new junction id

@@ -6,7 +6,7 @@
 #include "cs_common.cuh"
 
 struct CsArenaLayout {
-    size_t ds, node_list, qa, qb, far, s_node, s_agg, predmask, sigma, dep, bdone, frank, needm, stride;
+    size_t ds, node_list, qa, qb, far, s_node, s_agg, predmask, sigma, dep, bdone, frank, needm, jrank, stride;
     uint32_t rcap, qcap;
 };
 

@@ -83,6 +83,10 @@ struct CsShortest3Params {
     float delta, bin_scale;
 };
 
+// Per-chain seconds block (16-byte aligned): fwd[0..k], padding to a multiple of four floats, then bwdr[0..k] - both
+// direction arrays start on a 16-byte boundary, so a block is staged with 16-byte asynchronous copies.
+__host__ __device__ __forceinline__ uint32_t cs3_pb(uint32_t k) { return (k + 4u) & ~3u; }
+
 struct CsView {
     uint32_t far, sv, sF, k, id1, paf, cnt;  // sv / sF: offsets of the outward steps inside the chain's block
     uint32_t blk, nv;                        // the block: float offset into csec, number of floats
@@ -100,9 +104,9 @@ __device__ __forceinline__ CsView cs3_view(const CsV3Graph& g, const CsSrc3& S, 
         // the source sits inside a chain at position p (1-based): two links, toward A (0) and toward B (1)
         V.cnt = 1;
         V.blk = S.soff;
-        V.nv = 2 * (S.k + 1);
+        V.nv = cs3_pb(S.k) + S.k + 1;
         if (j == 0) {
-            V.sv = (S.k + 1) + (S.k - S.p + 1);
+            V.sv = cs3_pb(S.k) + (S.k - S.p + 1);
             V.sF = 0;
             V.k = S.p - 1;
             V.id1 = g.J + S.ibase + S.p - 2;
@@ -111,7 +115,7 @@ __device__ __forceinline__ CsView cs3_view(const CsV3Graph& g, const CsSrc3& S, 
             V.paf = S.posA;
         } else {
             V.sv = S.p;
-            V.sF = S.k + 1;
+            V.sF = cs3_pb(S.k);
             V.k = S.k - S.p;
             V.id1 = g.J + S.ibase + S.p;
             V.step = 1;
@@ -127,14 +131,14 @@ __device__ __forceinline__ CsView cs3_view(const CsV3Graph& g, const CsSrc3& S, 
     V.paf = (L.w >> 5) & 15u;
     V.cnt = (L.w >> 9) & 3u;
     V.blk = L.y;
-    V.nv = 2 * (k + 1);
+    V.nv = cs3_pb(k) + k + 1;
     if (dir == 0) {
         V.sv = 0;
-        V.sF = k + 1;
+        V.sF = cs3_pb(k);
         V.id1 = g.J + L.z;
         V.step = 1;
     } else {
-        V.sv = k + 1;
+        V.sv = cs3_pb(k);
         V.sF = 0;
         V.id1 = g.J + L.z + k - 1;
         V.step = -1;
@@ -144,7 +148,7 @@ __device__ __forceinline__ CsView cs3_view(const CsV3Graph& g, const CsSrc3& S, 
         V.far = g.J;
         if (dir == 0) {
             V.k = S.p - 1;
-            V.sF = (k + 1) + (k - S.p + 1);
+            V.sF = cs3_pb(k) + (k - S.p + 1);
             V.paf = 0;
         } else {
             V.k = k - S.p;
@@ -155,14 +159,28 @@ __device__ __forceinline__ CsView cs3_view(const CsV3Graph& g, const CsSrc3& S, 
     return V;
 }
 
-// The seconds of a chain (both directions, <= 2 * (CS3_KMAX + 1) floats) are copied with independent asynchronous 4-byte
-// copies (LDGSTS, no registers) into the lane's column of a shared-memory scratch; the sequential f32 walks then run at
-// shared-memory latency instead of one dependent L2 round trip per piece.
+// The seconds of a chain (both directions, <= cs3_pb(CS3_KMAX) + CS3_KMAX + 1 = 29 floats) are staged with independent
+// asynchronous 16-byte copies (LDGSTS.128, no registers) into the lane's column of 16-byte cells; the sequential f32 walks
+// then run at shared-memory latency instead of one dependent L2 round trip per piece.  Float i of the block sits in cell
+// i / 4 of the lane: cells[(i / 4) * 32 + lane], component i % 4.
+#ifndef CS3_STAGE16
+#define CS3_STAGE16 1
+#endif
 __device__ __forceinline__ void cs3_load_block(const CsV3Graph& g, const CsView& V, float* cb, uint32_t first, uint32_t count) {
+#if CS3_STAGE16
+    const uint32_t c0 = first >> 2, c1 = (first + count + 3u) >> 2;
+    const float* src = g.csec + V.blk;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(cb);
+    for (uint32_t c = c0; c < c1; ++c)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + c * 512u), "l"(src + 4u * c) : "memory");
+#else
     const float* src = g.csec + V.blk + first;
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(cb + first * 32);
-    for (uint32_t i = 0; i < count; ++i)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + i * 128u), "l"(src + i) : "memory");
+    for (uint32_t i = 0; i < count; ++i) {
+        const uint32_t e = first + i;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(cb + (e >> 2) * 128u + (e & 3u));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + i) : "memory");
+    }
+#endif
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
@@ -250,11 +268,11 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
     // per-warp shared memory: region A (4 KB): P2 bins | P3 candidates | P4 staged (node, cost) list | P5 node ids / costs;
     // region B (6 KB): P3 walk values | P5 per-node seeds -> credits; region C: P3 / P5 link list, link bytes, P5 outflow
     constexpr uint32_t NB = DT <= 3 ? CS3_NB3 : DT == 4 ? 96u : 24u;  // staged nodes per P5 sub-iteration
-    constexpr uint32_t WALK_BYTES = (CS3_KMAX + 2 + 28) * 32 * 4;
+    constexpr uint32_t WALK_BYTES = 8 * 32 * 16;  // the chain-block scratch: 8 cells of 16 bytes per lane
     constexpr uint32_t BYTES_A = CS3_NBINS * 4, BYTES_B = 2 * DT * NB * 8 > WALK_BYTES ? 2 * DT * NB * 8 : WALK_BYTES;
     constexpr uint32_t BYTES_C = 2 * DT * 32 * 8 + 256 * 2 + 256;
     constexpr uint32_t BYTES_W = BYTES_A + BYTES_B + BYTES_C;
-    static_assert(BYTES_B >= (CS3_KMAX + 2 + 28) * 32 * 4, "walk values and the chain block must fit region B");
+    static_assert(BYTES_B >= WALK_BYTES && ((CS3_KMAX + 4) & ~3) + CS3_KMAX + 1 <= 32, "the chain block must fit region B");
     static_assert(3 * NB * 4 <= BYTES_A && NB >= CS3_KMAX, "P5 node staging must fit region A");
     static_assert(CS3_LIST * 4 <= BYTES_A && CS3_LIST * 4 <= BYTES_B && CS3_LIST >= 32 * CS3_KMAX && CS3_NBINS % 32 == 0,
                   "P4 list: ids in region A, costs in region B");
@@ -274,8 +292,7 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
     uint32_t* s_ids = bins;                        // P5 staged nodes
     float* s_cst = reinterpret_cast<float*>(bins + NB);
     float* s_pcs = reinterpret_cast<float*>(bins + 2 * NB);
-    float* walk = reinterpret_cast<float*>(s_warp + BYTES_A);
-    float* cblk = walk + (CS3_KMAX + 2) * 32 + lane;  // the lane's column of the chain-block scratch (28 rows)
+    float* cblk = reinterpret_cast<float*>(s_warp + BYTES_A) + lane * 4;  // the lane's column of 16-byte cells (8 rows)
     uint16_t* ttab = reinterpret_cast<uint16_t*>(bins);  // P1: (owner lane | link << 8) of the batch's relaxations
     static_assert(32 * CS3_MAX_LINKS * 2 <= BYTES_A, "P1 task table must fit region A");
     double* s_crd = reinterpret_cast<double*>(s_warp + BYTES_A);
@@ -285,8 +302,7 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
     uint32_t* histN = s_hist_all[wic][0];
     uint32_t* histE = s_hist_all[wic][1];
     float* rankf = s_rank_all[wic];
-#define CS3_W(t) walk[(t) * 32 + lane]
-#define CS3_CB(i) cblk[(i) * 32]
+#define CS3_CB(i) cblk[((i) >> 2) * 128u + ((i) & 3u)]
     const CsWarpArena A = cs_arena(p.arena, p.lay, worker);
     uint8_t* linfo = A.bdone;          // [rcap][8] link bytes: T | tie2 << 4 | yhas << 5
     uint32_t* minsucc = A.node_list;   // [rcap] after P2: smallest rank that has this junction as a predecessor
@@ -294,6 +310,9 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
     // rank of the far junction}, written by the link's OWNER end (the earlier-settled one) for both ends
     uint4* cand = reinterpret_cast<uint4*>(p.arena + (size_t)worker * p.lay.stride + p.lay.frank);
     uint32_t* needm = reinterpret_cast<uint32_t*>(p.arena + (size_t)worker * p.lay.stride + p.lay.needm);  // [rcap]
+    // [rcap] {first link, links | in-degree << 8} of the junction at each settle rank: the later phases read it next to
+    // s_node / s_agg (one coalesced round trip) instead of chasing jinfo[s_node[r]]
+    uint2* jrank = reinterpret_cast<uint2*>(p.arena + (size_t)worker * p.lay.stride + p.lay.jrank);
     const CsV3Graph& g = p.g;
     const uint32_t J = g.J;
     const int D = DT <= 4 ? DT : p.D;  // instantiations up to 4 thresholds are exact: the threshold loops unroll without tests
@@ -371,22 +390,19 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                         const uint32_t idx = b0 + lane;
                         bool valid = idx < nc;
                         uint32_t v = 0, abits = 0, skip = 0xffffffffu;
+                        uint32_t off = 0, deg = 0;
                         if (valid) {
                             const uint2 it = cs_ld(&qc[idx]);
                             v = it.x & CS_NODE_MASK;
                             skip = (it.x >> CS_NODE_BITS) - 1u;
                             abits = it.y;
-                            valid = cs_ld(&A.ds[v].x) == abits;
-                        }
-                        uint32_t off = 0, deg = 0;
-                        if (valid) {
-                            if (v == J) {
-                                deg = 2;
-                            } else {
-                                const uint2 ji = __ldg(&g.jinfo[v]);
-                                off = ji.x;
-                                deg = ji.y & 0xffu;
-                            }
+                            // the staleness test and the junction record are independent loads: one round trip, not two
+                            const uint32_t cur = cs_ld(&A.ds[v].x);
+                            uint2 ji = make_uint2(0u, 2u);
+                            if (v != J) ji = __ldg(&g.jinfo[v]);
+                            valid = cur == abits;
+                            off = ji.x;
+                            deg = valid ? (ji.y & 0xffu) : 0u;
                         }
                         // One lane per LINK: the frontier holds few junctions at a time (about nine per batch on the
                         // 1M-node street graph), so the (junction, link) pairs of the batch are spread over the lanes and
@@ -572,7 +588,9 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                 cs_st(&A.sigma[rank], 0.0);
                 cs_st(&minsucc[rank], CS_NOSLOT);  // (node_list is dead from here on)
                 cs_st(&needm[rank], 0u);
-                edge_iters += node == J ? 2u : (__ldg(&g.jinfo[node]).y >> 8);
+                const uint2 ji = node == J ? make_uint2(0u, 2u | (2u << 8)) : __ldg(&g.jinfo[node]);
+                cs_st(&jrank[rank], ji);
+                edge_iters += ji.y >> 8;
             }
             __syncwarp();
         }
@@ -622,12 +640,9 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                     if constexpr (DT <= 3) cntN += 1ull << (16 * th);
                     else atomicAdd(&histN[th], 1u);
                 }
-                deg = 2;
-                if (v != J) {
-                    const uint2 ji = __ldg(&g.jinfo[v]);
-                    off = ji.x;
-                    deg = ji.y & 0xffu;
-                }
+                const uint2 ji = cs_ld(&jrank[r]);
+                off = ji.x;
+                deg = ji.y & 0xffu;
             }
             uint32_t inc = deg;
 #pragma unroll
@@ -900,12 +915,9 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                     v = cs_ld(&A.s_node[r]);
                     av = cs_ld(&A.s_agg[r]);
                     info8 = cs_ld(reinterpret_cast<const unsigned long long*>(linfo + (size_t)r * 8));
-                    deg = 2;
-                    if (v != J) {
-                        const uint2 ji = __ldg(&g.jinfo[v]);
-                        off = ji.x;
-                        deg = ji.y & 0xffu;
-                    }
+                    const uint2 ji = cs_ld(&jrank[r]);
+                    off = ji.x;
+                    deg = ji.y & 0xffu;
                 }
                 // the junctions of this chunk (the source is not a target)
                 __syncwarp();
@@ -980,12 +992,9 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                     aw = cs_ld(&A.s_agg[r]);
                     sigma_w = cs_ld(&A.sigma[r]);
                     nm = cs_ld(&needm[r]);
-                    deg = 2;
-                    if (w != J) {
-                        const uint2 ji = __ldg(&g.jinfo[w]);
-                        off = ji.x;
-                        deg = ji.y & 0xffu;
-                    }
+                    const uint2 ji = cs_ld(&jrank[r]);
+                    off = ji.x;
+                    deg = ji.y & 0xffu;
                 }
                 uint32_t inc = deg;
 #pragma unroll
@@ -1188,12 +1197,35 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                         }
                         // outflow into the junction (a handful of non-negative f64 terms per junction: the order of
                         // the shared-memory atomics does not matter beyond the last bit)
-                        if (go) {
+                        {
+                            // the links of a junction sit in consecutive lanes (at most CS3_MAX_LINKS = 8): a segmented
+                            // shuffle reduction and one plain add by the run's first lane replace per-link f64 atomics
+                            // on shared memory (compare-and-swap loops: 6.6 % of the samples in profiles/r01z)
+                            const uint32_t key = act ? jl : 64u + lane;
+                            const uint32_t kprev = __shfl_up_sync(CS_FULL, key, 1);
+                            const bool head = act && (lane == 0 || kprev != key);
+                            double ov[2 * DT];
 #pragma unroll
                             for (int i = 0; i < DT; ++i) {
-                                if (i < D) {
-                                    atomicAdd(&s_acc[i * 32 + jl], dl[i]);
-                                    atomicAdd(&s_acc[(DT + i) * 32 + jl], dlb[i]);
+                                ov[i] = go ? dl[i] : 0.0;
+                                ov[DT + i] = go ? dlb[i] : 0.0;
+                            }
+#pragma unroll
+                            for (int o = 1; o < (int)CS3_MAX_LINKS; o <<= 1) {
+                                const bool same = __shfl_down_sync(CS_FULL, key, o) == key && lane + o < 32u;
+#pragma unroll
+                                for (int q = 0; q < 2 * DT; ++q) {
+                                    const double t = __shfl_down_sync(CS_FULL, ov[q], o);
+                                    if (same) ov[q] += t;
+                                }
+                            }
+                            if (head) {
+#pragma unroll
+                                for (int i = 0; i < DT; ++i) {
+                                    if (i < D) {
+                                        s_acc[i * 32 + jl] += ov[i];
+                                        s_acc[(DT + i) * 32 + jl] += ov[DT + i];
+                                    }
                                 }
                             }
                         }
@@ -1261,7 +1293,6 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
             atomicAdd(&p.counters[CS_C_PHASE0 + 7], (unsigned long long)n_batches);  // 32-link batches
         }
     }
-#undef CS3_W
 #undef CS3_CB
 #undef CS3_BAR
 }
@@ -1291,7 +1322,7 @@ __global__ void cs_k_epilogue_shortest3(const double* __restrict__ acc_c, const 
 template <int DT>
 static constexpr uint32_t cs3_smem_bytes() {
     constexpr uint32_t NB = DT <= 3 ? CS3_NB3 : DT == 4 ? 96u : 24u;
-    constexpr uint32_t WALK_BYTES = (CS3_KMAX + 2 + 28) * 32 * 4;
+    constexpr uint32_t WALK_BYTES = 8 * 32 * 16;
     constexpr uint32_t B = 2 * DT * NB * 8 > WALK_BYTES ? 2 * DT * NB * 8 : WALK_BYTES;
     return cs3_warps<DT>() * (CS3_NBINS * 4 + B + 2 * DT * 32 * 8 + 256 * 2 + 256);
 }

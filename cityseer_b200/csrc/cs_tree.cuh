@@ -45,6 +45,8 @@ __global__ void cs_k_tree_segment(CsTreeParams p) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     CsHeap h;
     h.d = p.heap;
+    h.sm = nullptr;
+    h.nsm = 0;
     h.len = 0;
     uint32_t nv = 0, ne = 0;
     p.agg[p.src] = 0.0f;
@@ -91,6 +93,8 @@ __global__ void cs_k_tree_angular(CsTreeParams p) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     CsHeap h;
     h.d = p.heap;
+    h.sm = nullptr;
+    h.nsm = 0;
     h.len = 0;
     uint32_t nv = 0;
     p.order[nv++] = p.src;
