@@ -750,8 +750,9 @@ static int finish_call(cs_graph* g, double* out, int out_on_device, size_t elems
     if (herr == CS_ERR_QUEUE_OVERFLOW)
         return cs_fail("search queue overflow (capacity %u); raise reach_capacity via cs_graph_configure", g->lay.qcap);
     if (herr == CS_ERR_ZERO_TIE)
-        return cs_fail("zero-length edge between nodes that tie on (seconds, index): settle order undefined; remove "
-                       "zero-length edges (tools.graphs.nx_simple_geoms does) or select the global-arena kernel");
+        return cs_fail("zero-second edge between nodes that tie on (seconds, index): the reference settles such pairs in heap "
+                       "order; remove zero-length edges (tools.graphs.nx_simple_geoms does) / give transport edges a "
+                       "positive travel time");
     if (herr == CS_ERR_PRED_OVERFLOW)
         return cs_fail("a dual state acquired more than %d tied predecessors (unsupported)", CS_ANG_MAXPRED);
     if (herr) return cs_fail("device error %d", herr);

@@ -176,6 +176,10 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
                         }
                     }
                 }
+                // A reached node without an earlier-settled predecessor: its predecessor ties with it on (seconds, index)
+                // through a zero-second edge, and the reference settles such pairs in heap order.  Outside this kernel's
+                // contract: fail loudly (and never leave sigma at zero, which the nodes behind it would wait on).
+                if (v != src && pmask_c == 0) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);
                 uint32_t amask = 0;
                 for (uint32_t mm = pmask_c; mm; mm &= mm - 1) amask |= 1u << (cj[__ffs(mm) - 1] & 0xffu);
                 cs_st(&A.predmask[r], amask);
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
                         s += sg;
                     }
                     if (ok) {
-                        cs_st(&A.sigma[r], s);
+                        cs_st(&A.sigma[r], pmask_c ? s : 1.0);
                         pending = false;
                     }
                 }

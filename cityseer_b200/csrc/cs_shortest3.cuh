@@ -30,7 +30,9 @@
 #ifndef CS3_MIN_BLOCKS
 #define CS3_MIN_BLOCKS 2
 #endif
-#define CS3_WORKERS_PER_SM 16  // resident warps per SM of either shape
+#ifndef CS3_WORKERS_PER_SM
+#define CS3_WORKERS_PER_SM CS3_WARPS_WIDE  // resident warps per SM of either shape
+#endif
 template <int DT>
 __host__ __device__ constexpr uint32_t cs3_warps() { return DT <= 4 ? CS3_WARPS_WIDE : CS3_WARPS; }
 template <int DT>

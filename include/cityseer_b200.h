@@ -40,7 +40,9 @@ typedef struct cs_stats {
     uint64_t phase_cycles[8]; /* SM clock cycles summed over workers per kernel phase (search, order, predecessors,
                                  closeness, dependencies, reset); chain-contracted kernel: [6] dependency chunks,
                                  [7] 32-link batches of the dependency pass */
-    uint64_t fallback_sources; /* reserved (0) */
+    uint64_t fallback_sources; /* segment_centrality: sources whose tree has parents with bit-equal seconds competing for a
+                                 node; they are served by the heap-order replay launch (centrality.rs:1589 resolves such
+                                 ties by BinaryHeap pop order) */
     uint32_t smem_bytes;      /* reserved (0) */
     uint32_t ctas_per_sm;     /* reserved (0) */
     uint32_t reach_capacity;  /* nodes (junctions, for the chain-contracted kernel) a source may reach: arena capacity */
@@ -65,7 +67,9 @@ void cs_host_free(void* ptr);
  *                             The coordinates only order the device copy of the graph along a Hilbert curve so that
  *                             the nodes one source reaches are contiguous in memory; results do not depend on them.
  *   edge arrays [edge_bound]: exists, src, dst, edge_idx (payload key), length, angle_sum, imp_factor,
- *                             seconds (NaN for street edges), shared_key (dual: id of shared_primal_node_key, else -1),
+ *                             seconds (NaN for street edges; finite >= 0 for transport edges, graph.rs:946-985: the
+ *                             value edge_travel_seconds returns at any speed, centrality.rs:988-990, length NaN),
+ *                             shared_key (dual: id of shared_primal_node_key, else -1),
  *                             stamp (insertion sequence; larger = newer)
  */
 cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_exists, const uint8_t* live, const float* weight,

@@ -117,7 +117,7 @@ def test_hilly_dual_simplest(oracle_mod):
     assert res.stats["settled"] == cnt["settled"] and res.stats["edge_iters"] == cnt["edge_iters"]
 
 
-def transport_network():
+def transport_network(extra=()):
     """mock_graph plus two 'stops' joined by fast transport edges (explicit seconds, both directions)."""
     _g, _n, _e, base = H.primal_ns()
     f = base.frozen()
@@ -129,7 +129,7 @@ def transport_network():
         ns.add_street_edge(a, b, int(f.edge_idx[e]), a, b,
                            f"LINESTRING({f.xs[a]} {f.ys[a]}, {f.xs[b]} {f.ys[b]})")  # fmt: skip
     far_a, far_b = 0, int(np.argmax(np.hypot(f.xs - f.xs[0], f.ys - f.ys[0])))
-    for a, b, sec in ((far_a, far_b, 40.0), (far_b, far_a, 55.0), (3, 30, 0.0), (30, 3, 12.5)):
+    for a, b, sec in ((far_a, far_b, 40.0), (far_b, far_a, 55.0), (3, 30, 0.5), (30, 3, 12.5)) + tuple(extra):
         ns.add_transport_edge(a, b, 7, a, b, sec)
     return ns
 
@@ -146,6 +146,18 @@ def test_transport_edges_shortest(oracle_mod, kernel):
     ref, _ = oracle_mod.OracleGraph(f).centrality_shortest(d, b, s, 2.0, n_threads=8)
     assert np.array_equal(res._out[0], ref[0])
     np.testing.assert_allclose(res._out, ref, rtol=RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("kernel", [0, 1], ids=["auto", "arena-kernel"])
+def test_zero_second_edge_fails_loudly(kernel):
+    # a zero-second edge makes its two ends tie on seconds; the reference orders them by heap pop order.  The device
+    # refuses the call instead of guessing (and must not hang: the nodes behind the tie wait for its sigma)
+    ns = transport_network(extra=((5, 40, 0.0),))
+    set_kernel(kernel)
+    with pytest.raises(ValueError, match="zero-second edge"):
+        ns.centrality_shortest(distances=[400, 800], pbar_disabled=True)
+    ns2 = transport_network()  # the same graph without it computes (fresh arena after the failure)
+    ns2.centrality_shortest(distances=[400, 800], pbar_disabled=True)
 
 
 def test_transport_edge_validation():
