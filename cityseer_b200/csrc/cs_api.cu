@@ -77,6 +77,7 @@ struct cs_graph {
     int arena_D = 0;
     int arena_kind = -1;
     uint32_t workers = 0, cfg_workers = 0, cfg_rcap = 0;
+    bool rcap_user = false;  // reach_capacity pinned by cs_graph_configure: overflow is an error, not a reason to grow
     float cfg_delta = 0.f;
     float mean_edge_len = 0.f;
     cudaStream_t stream = nullptr, side_stream = nullptr, own_stream = nullptr;
@@ -459,7 +460,10 @@ extern "C" void cs_graph_destroy(cs_graph* g) {
 
 extern "C" int cs_graph_configure(cs_graph* g, uint32_t reach_capacity, float delta_seconds, uint32_t workers) {
     if (!g) return cs_fail("null graph");
-    if (reach_capacity) g->cfg_rcap = reach_capacity;
+    if (reach_capacity) {
+        g->cfg_rcap = reach_capacity;
+        g->rcap_user = true;
+    }
     if (delta_seconds > 0.f) g->cfg_delta = delta_seconds;
     if (workers) g->cfg_workers = workers;
     if (reach_capacity || workers) g->arena_kind = -1;  // force re-allocation
@@ -499,6 +503,24 @@ extern "C" uint64_t cs_progress(cs_graph* g) {
 }
 
 // ------------------------------------------------------------------------------------------------ arena
+// Default capacity of a search in reached nodes (junctions for the chain kernel, states for the angular one).  A call
+// that overflows it is repeated with four times the capacity (grow_after_overflow) unless the caller pinned the value
+// with cs_graph_configure: the arena then only grows for graphs and distances that need it (the reference's own 20 km
+// Greater-London runs reach 69 k nodes).
+#define CS_DEFAULT_RCAP (1u << 14)
+
+// After a failed call: true when the failure was an arena overflow and the capacity could be raised (the caller repeats
+// the call; nothing of the failed attempt has reached a caller-owned buffer unless it asked to accumulate).
+static bool grow_after_overflow(cs_graph* g, size_t nstates, uint32_t current) {
+    if (!g || g->rcap_user) return false;
+    if (g->last_herr != CS_ERR_REACH_OVERFLOW && g->last_herr != CS_ERR_QUEUE_OVERFLOW) return false;
+    g->last_herr = 0;
+    if ((size_t)current >= nstates) return false;
+    g->cfg_rcap = (uint32_t)std::min<size_t>(nstates, (size_t)current * 4);
+    g->arena_kind = -1;
+    return true;
+}
+
 // kind 0 = shortest, 1 = segment, 2 = simplest (two states per node), 3 = chain-contracted shortest (junction states)
 static int ensure_arena(cs_graph* g, int kind, int D) {
     if (g->d_arena && g->arena_kind == kind && g->arena_D >= D) return 0;
@@ -507,7 +529,7 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
         g->d_arena = nullptr;
     }
     const size_t nstates = kind == 2 ? (size_t)g->n * 2 : kind == 3 ? (size_t)g->v3_J + 1 : g->n;
-    uint32_t rcap = g->cfg_rcap ? g->cfg_rcap : (1u << 16);
+    uint32_t rcap = g->cfg_rcap ? g->cfg_rcap : CS_DEFAULT_RCAP;
     rcap = (uint32_t)std::min<size_t>(rcap, nstates);
     rcap = std::max(rcap, 32u);
     const uint32_t qcap = rcap * 2 + 64;
@@ -573,7 +595,7 @@ static int ensure_arena_angular(cs_graph* g, int D) {
         g->d_arena = nullptr;
     }
     const size_t nstates = (size_t)g->n * 2;
-    uint32_t rcap = g->cfg_rcap ? g->cfg_rcap : (1u << 16);
+    uint32_t rcap = g->cfg_rcap ? g->cfg_rcap : CS_DEFAULT_RCAP;
     rcap = (uint32_t)std::min<size_t>(std::max<size_t>(rcap, 64), nstates);
     const uint32_t hcap = rcap * 4 + 64;
     uint32_t workers = g->cfg_workers ? g->cfg_workers : (uint32_t)g->sm_count * CS_ANG_MIN_BLOCKS * CS_WARPS_PER_CTA;
@@ -1022,9 +1044,14 @@ extern "C" int cs_centrality_shortest(cs_graph* g, int D, const uint32_t* distan
                                       const float* source_wt, const uint8_t* eligible, double* out, int out_on_device,
                                       int accumulate, cs_stats* stats) {
     if (!out) return cs_fail("null output");
-    return run_shortest(g, D, distances, betas, seconds, speed_m_s, tolerance, compute_closeness, compute_betweenness,
-                        n_sources, sources, source_wt, eligible, out, out_on_device, accumulate, stats, nullptr, nullptr,
-                        nullptr);
+    for (;;) {
+        const int rc = run_shortest(g, D, distances, betas, seconds, speed_m_s, tolerance, compute_closeness,
+                                    compute_betweenness, n_sources, sources, source_wt, eligible, out, out_on_device,
+                                    accumulate, stats, nullptr, nullptr, nullptr);
+        if (!rc || accumulate || !g) return rc;
+        const size_t nstates = g->last_kernel == 3 ? (size_t)g->v3_J + 1 : g->n;
+        if (!grow_after_overflow(g, nstates, g->lay.rcap)) return rc;
+    }
 }
 
 // betweenness_od_shortest (centrality.rs:2419-2540).  `out` is the [7][D][node_bound] layout of centrality_shortest with
@@ -1036,8 +1063,12 @@ extern "C" int cs_betweenness_od_shortest(cs_graph* g, int D, const uint32_t* di
     if (!out) return cs_fail("null output");
     if (!sources || !od_off || (od_off[n_sources] && (!od_dst || !od_w))) return cs_fail("null OD arrays");
     std::vector<float> ones(std::max<uint64_t>(n_sources, 1), 1.0f);
-    return run_shortest(g, D, distances, betas, seconds, speed_m_s, tolerance, 0, 1, n_sources, sources, ones.data(), nullptr,
-                        out, out_on_device, 0, stats, nullptr, nullptr, nullptr, od_off, od_dst, od_w);
+    for (;;) {
+        const int rc = run_shortest(g, D, distances, betas, seconds, speed_m_s, tolerance, 0, 1, n_sources, sources,
+                                    ones.data(), nullptr, out, out_on_device, 0, stats, nullptr, nullptr, nullptr, od_off,
+                                    od_dst, od_w);
+        if (!rc || !g || !grow_after_overflow(g, g->n, g->lay.rcap)) return rc;
+    }
 }
 
 extern "C" int cs_shortest_search(cs_graph* g, uint32_t src, uint32_t max_seconds, float speed_m_s, float tolerance,

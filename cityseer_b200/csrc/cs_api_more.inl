@@ -67,6 +67,7 @@ extern "C" int cs_dijkstra_tree_shortest(cs_graph* g, uint32_t src, uint32_t max
     p.dump_agg = d_agg;
     p.dump_count = d_count;
     p.replay = 1;  // one source: always settle equal keys in the reference's heap order
+    p.src_per_cta = 1;
     if (segment_smem_optin(g)) return 1;
     cs_k_segment<1><<<1, CS_SEG_WARPS * 32, CS_SEG_SMEM_BYTES, g->stream>>>(p);
     int rc = 0;
@@ -95,9 +96,9 @@ extern "C" int cs_dijkstra_tree_shortest(cs_graph* g, uint32_t src, uint32_t max
 }
 
 // ------------------------------------------------------------------------------------------------ segment
-extern "C" int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
-                                     float speed_m_s, int compute_closeness, int compute_betweenness, uint64_t n_sources,
-                                     const uint32_t* sources, double* out, int out_on_device, int accumulate, cs_stats* stats) {
+static int run_segment(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
+                       float speed_m_s, int compute_closeness, int compute_betweenness, uint64_t n_sources,
+                       const uint32_t* sources, double* out, int out_on_device, int accumulate, cs_stats* stats) {
     if (!g) return cs_fail("null graph");
     if (!out) return cs_fail("null output");
     if (check_thresholds(D, seconds)) return 1;
@@ -150,8 +151,11 @@ extern "C" int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distanc
     }
     p.redo_list = g->d_redo;
     auto launch = [&](uint64_t m) -> int {
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(g->workers / CS_SEG_WARPS, (m + CS_SEG_WARPS - 1) / CS_SEG_WARPS);
-        if (grid == 0) return 0;
+        const uint32_t ctas = g->workers / CS_SEG_WARPS;
+        if (ctas == 0 || m == 0) return 0;
+        // few sources (the replay list): spread them over all CTAs, one warp each; else 32 consecutive sources per CTA
+        p.src_per_cta = (uint32_t)std::min<uint64_t>(CS_SEG_WARPS, (m + ctas - 1) / ctas);
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(ctas, (m + p.src_per_cta - 1) / p.src_per_cta);
         const int threads = CS_SEG_WARPS * 32;
         const size_t sm = CS_SEG_SMEM_BYTES;
         if (D == 1) cs_k_segment<1><<<grid, threads, sm, g->stream>>>(p);
@@ -187,12 +191,22 @@ extern "C" int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distanc
     return finish_call(g, out, out_on_device, elems, d_out, stats, launches);
 }
 
+extern "C" int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
+                                     float speed_m_s, int compute_closeness, int compute_betweenness, uint64_t n_sources,
+                                     const uint32_t* sources, double* out, int out_on_device, int accumulate, cs_stats* stats) {
+    for (;;) {
+        const int rc = run_segment(g, D, distances, betas, seconds, speed_m_s, compute_closeness, compute_betweenness,
+                                   n_sources, sources, out, out_on_device, accumulate, stats);
+        // the segment kernel adds straight into `out`: a failed attempt can only be repeated when it started from zero
+        if (!rc || accumulate || !g || !grow_after_overflow(g, g->n, g->lay.rcap)) return rc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ simplest
-extern "C" int cs_centrality_simplest(cs_graph* g, int D, const uint32_t* distances, const uint32_t* seconds, float speed_m_s,
-                                      float tolerance, float angular_scaling_unit, float farness_scaling_offset,
-                                      int compute_closeness, int compute_betweenness, uint64_t n_sources,
-                                      const uint32_t* sources, const float* source_wt, const uint8_t* eligible, double* out,
-                                      int out_on_device, int accumulate, cs_stats* stats) {
+static int run_simplest(cs_graph* g, int D, const uint32_t* distances, const uint32_t* seconds, float speed_m_s,
+                        float tolerance, float angular_scaling_unit, float farness_scaling_offset, int compute_closeness,
+                        int compute_betweenness, uint64_t n_sources, const uint32_t* sources, const float* source_wt,
+                        const uint8_t* eligible, double* out, int out_on_device, int accumulate, cs_stats* stats) {
     (void)distances;
     if (!g) return cs_fail("null graph");
     if (!out) return cs_fail("null output");
@@ -260,4 +274,17 @@ extern "C" int cs_centrality_simplest(cs_graph* g, int D, const uint32_t* distan
     }
     CS_CUDA(cudaEventRecord(g->ev[2], g->stream));
     return finish_call(g, out, out_on_device, elems, d_out, stats, launches);
+}
+
+extern "C" int cs_centrality_simplest(cs_graph* g, int D, const uint32_t* distances, const uint32_t* seconds, float speed_m_s,
+                                      float tolerance, float angular_scaling_unit, float farness_scaling_offset,
+                                      int compute_closeness, int compute_betweenness, uint64_t n_sources,
+                                      const uint32_t* sources, const float* source_wt, const uint8_t* eligible, double* out,
+                                      int out_on_device, int accumulate, cs_stats* stats) {
+    for (;;) {
+        const int rc = run_simplest(g, D, distances, seconds, speed_m_s, tolerance, angular_scaling_unit,
+                                    farness_scaling_offset, compute_closeness, compute_betweenness, n_sources, sources,
+                                    source_wt, eligible, out, out_on_device, accumulate, stats);
+        if (!rc || accumulate || !g || !grow_after_overflow(g, (size_t)g->n * 2, g->ang_lay.rcap)) return rc;
+    }
 }

@@ -60,7 +60,11 @@ __device__ __forceinline__ void cs_red_add(double* p, double v) {
 #ifdef CS_EXPERIMENT_NO_RED  // measurement only: how much of the time the f64 scatter costs
     if (v == -1.2345) *p = v;
 #else
+#ifdef CS_RED_NOCLOBBER  // experiment: let the compiler move independent work across the reduction
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v));
+#else
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+#endif
 #endif
 }
 // f32 exp as the reference's platform libm computes it.  Rust's f32::exp calls expf; on Linux that is glibc's table-driven
@@ -81,16 +85,22 @@ __device__ __forceinline__ float cs_expf_libm(float x) {
     if (!(x >= -104.0f)) return x != x ? x : 0.0f;  // underflow (and NaN)
     if (x > 88.72284f) return __uint_as_float(CS_INF_BITS);
     const double z = 0x1.71547652b82fep+0 * 32.0 * (double)x;
-    const long long ki = __double2ll_rn(z);
-    const double r = z - (double)ki;
-    const unsigned long long t = __ldg(&cs_exp2f_tab[ki & 31]) + ((unsigned long long)ki << 47);
+    // round to nearest integer with the 1.5 * 2^52 shift (glibc's non-intrinsic path): the integer sits in the low
+    // mantissa bits of kd + shift
+    const double shift = 0x1.8p52;
+    double kd = __dadd_rn(z, shift);
+    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+    kd = __dadd_rn(kd, -shift);
+    const double r = __dadd_rn(z, -kd);
+    const unsigned long long t = __ldg(&cs_exp2f_tab[ki & 31ull]) + (ki << 47);
     const double s = __longlong_as_double((long long)t);
     const double c0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0, c1 = 0x1.ebfce50fac4f3p-3 / 32.0 / 32.0;
     const double c2 = 0x1.62e42ff0c52d6p-1 / 32.0;
-    const double zz = c0 * r + c1;
+    // fused or unfused does not matter for the f32 result (the double carries ~2^-34 relative error before rounding)
+    const double zz = fma(c0, r, c1);
     const double r2 = r * r;
-    double y = c2 * r + 1.0;
-    y = zz * r2 + y;
+    double y = fma(c2, r, 1.0);
+    y = fma(zz, r2, y);
     y = y * s;
     return (float)y;
 }

@@ -9,6 +9,7 @@
 //          sum over strict descendants `to > src` of auc(to).
 #pragma once
 #include "cs_search.cuh"
+#include "cs_heap.cuh"
 
 struct CsSegmentParams {
     CsGraphDev g;
@@ -36,68 +37,14 @@ struct CsSegmentParams {
     // the search is replayed by one lane with the Rust heap (cs_seg_replay) and parents are ordered by its pop sequence.
     int replay;
     uint32_t* redo_list;
+    // sources a CTA takes per round (1 .. CS_SEG_WARPS; warps beyond it idle at the barriers): a short replay list is
+    // spread over all SMs instead of filling a few CTAs with 32 serial heap replays each
+    uint32_t src_per_cta;
 };
 
-// ---- Rust std::collections::BinaryHeap (max-heap on the reversed f32 order, centrality.rs:358-386) over (rank, seconds
-// bits) items: the first CS_SEG_HEAP_SMEM entries (the levels every sift touches) live in the warp's shared-memory bins,
-// the rest in the arena.  Same sift rules as cs_simplest.cuh's CsHeap (push = sift_up; pop = swap in the last element,
-// sift_down_to_bottom preferring the right child on ties, then sift_up).
+// The heap of the replay (cs_heap.cuh): the first CS_SEG_HEAP_SMEM entries in the warp's shared-memory bins, the arena
+// beyond that.
 #define CS_SEG_HEAP_SMEM (CS_NBINS / 2)
-struct CsSegHeap {
-    uint2* sm;
-    uint2* gl;
-    uint32_t len;
-    __device__ __forceinline__ uint2 get(uint32_t i) const { return i < CS_SEG_HEAP_SMEM ? sm[i] : cs_ld(&gl[i]); }
-    __device__ __forceinline__ void set(uint32_t i, uint2 v) {
-        if (i < CS_SEG_HEAP_SMEM) sm[i] = v;
-        else cs_st(&gl[i], v);
-    }
-    __device__ __forceinline__ void sift_up(uint32_t pos) {
-        const uint2 hole = get(pos);
-        while (pos > 0) {
-            const uint32_t parent = (pos - 1) / 2;
-            const uint2 pv = get(parent);
-            if (hole.y >= pv.y) break;  // hole <= parent in the reversed order
-            set(pos, pv);
-            pos = parent;
-        }
-        set(pos, hole);
-    }
-    __device__ __forceinline__ void push(uint32_t item, uint32_t bits) {
-        set(len, make_uint2(item, bits));
-        sift_up(len);
-        ++len;
-    }
-    __device__ __forceinline__ uint2 pop() {
-        uint2 item = get(--len);
-        if (len > 0) {
-            const uint2 root = get(0);
-            set(0, item);
-            item = root;
-            const uint32_t end = len;
-            uint32_t pos = 0, child = 1;
-            const uint2 hole = get(0);
-            while (end >= 2 && child <= end - 2) {
-                const uint2 l = get(child), r = get(child + 1);
-                uint2 c = l;
-                if (l.y >= r.y) {  // left <= right: take the right child
-                    child += 1;
-                    c = r;
-                }
-                set(pos, c);
-                pos = child;
-                child = 2 * pos + 1;
-            }
-            if (child == end - 1) {
-                set(pos, get(child));
-                pos = child;
-            }
-            set(pos, hole);
-            sift_up(pos);
-        }
-        return item;
-    }
-};
 
 // Replays dijkstra_tree_segment's heap loop (centrality.rs:1538-1609) over the reached set and records the pop sequence
 // number of every settled node in popseq[rank].  Lane 0 only; the other lanes help with the initialisation.
@@ -110,16 +57,14 @@ __device__ __forceinline__ void cs_seg_replay(const CsGraphDev& g, const CsWarpA
     }
     __syncwarp();
     if (lane == 0) {
-        CsSegHeap h;
-        h.sm = reinterpret_cast<uint2*>(smem_words);
-        h.gl = A.qa;  // qa, qb and far are contiguous and dead after the order pass
-        h.len = 0;
+        CsHeap h;
+        cs_heap_init(h, smem_words, CS_SEG_HEAP_SMEM, A.qa);  // qa, qb and far are contiguous and dead after the order pass
         const uint32_t cap = 3u * A.qcap;
         uint32_t seq = 0;
         cs_st(&run_agg[0], 0.0f);
-        h.push(0u, 0u);
+        cs_heap_push(h, 0u, 0u);
         while (h.len > 0) {
-            const uint32_t r = h.pop().x;
+            const uint32_t r = cs_heap_pop(h).x;
             if (cs_ld(&popseq[r]) != CS_NOSLOT) continue;  // lazy deletion (:1545)
             cs_st(&popseq[r], seq++);
             const uint32_t cur = cs_ld(&A.s_node[r]);
@@ -141,7 +86,7 @@ __device__ __forceinline__ void cs_seg_replay(const CsGraphDev& g, const CsWarpA
                         fail = CS_ERR_QUEUE_OVERFLOW;
                         break;
                     }
-                    h.push(dnb.y, __float_as_uint(ts));
+                    cs_heap_push(h, dnb.y, __float_as_uint(ts));
                 }
             }
             if (fail) break;
@@ -202,13 +147,13 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            s_base = atomicAdd(&p.counters[CS_C_NEXT], (unsigned long long)CS_SEG_WARPS);
+            s_base = atomicAdd(&p.counters[CS_C_NEXT], (unsigned long long)p.src_per_cta);
             s_err = *reinterpret_cast<volatile int*>(p.error);
         }
         __syncthreads();
         if (s_base >= p.n_sources || s_err != 0) break;
         const unsigned long long si = s_base + wic;
-        bool run = si < p.n_sources;  // an idle warp still meets the barriers; its R is 0 and every loop below is empty
+        bool run = wic < p.src_per_cta && si < p.n_sources;  // an idle warp still meets the barriers; its loops are empty
         const uint32_t src = run ? __ldg(&p.sources[si]) : 0u;
 
         unsigned long long relax = 0, edge_iters = 0, n_ci = 0;

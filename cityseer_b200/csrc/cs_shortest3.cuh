@@ -217,6 +217,14 @@ __device__ __forceinline__ bool cs3_other_kept(float c_own, float c_oth, bool ow
     return true;
 }
 
+// L2 prefetch of per-rank state a later chunk will read.  The per-warp arenas of the resident warps (about 150 KB per
+// source, 2 368 warps) exceed the L2, so what the predecessor pass wrote has mostly gone to DRAM by the time the dependency
+// pass walks back over it: each lane touches one rank PF ranks ahead, no registers, nothing waits on it.
+#ifndef CS3_PREFETCH
+#define CS3_PREFETCH 96
+#endif
+__device__ __forceinline__ void cs3_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // one copy of the f64 exponential (the beta-weighted seeds, centrality.rs:1805) instead of one per call site and
 // threshold: the dependency phase has to stay inside the instruction cache
 __device__ __noinline__ double cs3_exp(double x) { return exp(x); }
@@ -910,6 +918,14 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
             cycles_wt = __fdiv_rn(wt, __ldg(&g.weight[S.id]));  // centrality.rs:1730
             for (uint32_t b0 = 0; b0 < R; b0 += 32) {
                 const uint32_t r = b0 + lane;
+#if CS3_PREFETCH
+                if (r + CS3_PREFETCH < R) {
+                    cs3_prefetch(&A.s_node[r + CS3_PREFETCH]);
+                    cs3_prefetch(&A.s_agg[r + CS3_PREFETCH]);
+                    cs3_prefetch(&jrank[r + CS3_PREFETCH]);
+                    cs3_prefetch(linfo + (size_t)(r + CS3_PREFETCH) * 8);
+                }
+#endif
                 uint32_t v = 0, off = 0, deg = 0;
                 float av = 0.f;
                 unsigned long long info8 = 0ull;
@@ -980,6 +996,21 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
             int hi = (int)R - 1;
             while (hi >= 0) {
                 ++n_chunks;
+#if CS3_PREFETCH
+                {
+                    const int pr = hi - (int)CS3_PREFETCH - (int)lane;
+                    if (pr >= 0) {
+                        cs3_prefetch(&minsucc[pr]);
+                        cs3_prefetch(&A.s_node[pr]);
+                        cs3_prefetch(&A.s_agg[pr]);
+                        cs3_prefetch(&A.sigma[pr]);
+                        cs3_prefetch(&needm[pr]);
+                        cs3_prefetch(&jrank[pr]);
+                        cs3_prefetch(linfo + (size_t)pr * 8);
+                        cs3_prefetch(&cand[(size_t)pr * 8]);
+                    }
+                }
+#endif
                 const int rr = hi - (int)lane;
                 const uint32_t ms = rr >= 0 ? cs_ld(&minsucc[rr]) : 0u;
                 const uint32_t badm = __ballot_sync(CS_FULL, rr < 0 || ms <= (uint32_t)hi);

@@ -10,6 +10,7 @@
 // does.  Closeness and the Brandes accumulation afterwards are data-parallel over the settled states.
 #pragma once
 #include "cs_common.cuh"
+#include "cs_heap.cuh"
 
 #define CS_ANG_MAXPRED 8
 #define CS_VISITED 0x80000000u
@@ -39,71 +40,6 @@ struct CsSimplestParams {
 };
 
 enum { CS_ERR_PRED_OVERFLOW = 3 };
-
-// The heap of one search.  Its first `nsm` entries - the levels every sift passes through - live in shared memory, the
-// rest in the warp's arena: a pop walks ~log2(len) levels with two dependent reads each, which at L2 latency was most of
-// the angular kernel's time (one lane, ~3 000 pops per source).
-struct CsHeap {
-    uint2* d;   // {state, metric bits}; touched by one lane only
-    uint2* sm;  // shared-memory image of entries [0, nsm)
-    uint32_t nsm;
-    uint32_t len;
-    __device__ __forceinline__ uint2 get(uint32_t i) const { return i < nsm ? sm[i] : d[i]; }
-    __device__ __forceinline__ void set(uint32_t i, uint2 v) {
-        if (i < nsm) sm[i] = v;
-        else d[i] = v;
-    }
-};
-// Ord of the reference's NodeDistance (reversed f32 total order, centrality.rs:363-370): x <= y <=> x.metric >= y.metric.
-// All metrics here are non-negative floats, whose total order equals the unsigned order of their bit patterns.
-__device__ __forceinline__ bool cs_heap_le(uint2 a, uint2 b) { return a.y >= b.y; }
-__device__ __forceinline__ void cs_heap_sift_up(CsHeap& h, uint32_t start, uint32_t pos) {
-    const uint2 hole = h.get(pos);
-    while (pos > start) {
-        const uint32_t parent = (pos - 1) / 2;
-        const uint2 pv = h.get(parent);
-        if (cs_heap_le(hole, pv)) break;
-        h.set(pos, pv);
-        pos = parent;
-    }
-    h.set(pos, hole);
-}
-__device__ __forceinline__ void cs_heap_push(CsHeap& h, uint32_t state, uint32_t metric_bits) {
-    h.set(h.len, make_uint2(state, metric_bits));
-    cs_heap_sift_up(h, 0, h.len);
-    h.len++;
-}
-__device__ __forceinline__ uint2 cs_heap_pop(CsHeap& h) {
-    uint2 item = h.get(--h.len);
-    if (h.len > 0) {
-        const uint2 root = h.get(0);
-        h.set(0, item);
-        item = root;
-        // sift_down_to_bottom(0), then sift_up from the bottom (Rust std BinaryHeap::pop)
-        const uint32_t end = h.len;
-        uint32_t pos = 0;
-        const uint2 hole = h.get(0);
-        uint32_t child = 1;
-        while (end >= 2 && child <= end - 2) {
-            const uint2 l = h.get(child), r = h.get(child + 1);
-            uint2 c = l;
-            if (cs_heap_le(l, r)) {
-                child += 1;
-                c = r;
-            }
-            h.set(pos, c);
-            pos = child;
-            child = 2 * pos + 1;
-        }
-        if (child == end - 1) {
-            h.set(pos, h.get(child));
-            pos = child;
-        }
-        h.set(pos, hole);
-        cs_heap_sift_up(h, 0, pos);
-    }
-    return item;
-}
 
 __global__ void cs_k_init_ang(uint8_t* arena, size_t stride, size_t ds_off, size_t n_states, size_t dn_off, size_t n_nodes) {
     uint8_t* base = arena + (size_t)blockIdx.y * stride;
@@ -143,9 +79,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_ANG_MIN_BLOCKS) cs_k
     uint32_t* pending = reinterpret_cast<uint32_t*>(base + p.lay.pending);
     __shared__ uint2 s_heap[CS_WARPS_PER_CTA][CS_ANG_HEAP_SMEM];
     CsHeap heap;
-    heap.d = reinterpret_cast<uint2*>(base + p.lay.heap);
-    heap.sm = s_heap[threadIdx.x >> 5];
-    heap.nsm = CS_ANG_HEAP_SMEM;
+    cs_heap_init(heap, s_heap[threadIdx.x >> 5], CS_ANG_HEAP_SMEM, reinterpret_cast<uint2*>(base + p.lay.heap));
     const uint32_t rcap = p.lay.rcap, hcap = p.lay.hcap;
     const int D = p.D;
     const size_t n = p.n;
@@ -165,7 +99,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_ANG_MIN_BLOCKS) cs_k
         uint32_t nslots = 2, nvisited = 0;
         int fail = 0;
         unsigned long long edge_iters = 0;
-        heap.len = 0;
+        cs_heap_clear(heap);
         if (lane == 0) {
             cs_st(&dn[src], make_uint2(0u, 0u));
             for (uint32_t slot = 0; slot < 2; ++slot) {

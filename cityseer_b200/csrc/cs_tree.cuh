@@ -44,10 +44,7 @@ __global__ void cs_k_fill_u32(uint32_t* p, size_t n, uint32_t v) {
 __global__ void cs_k_tree_segment(CsTreeParams p) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     CsHeap h;
-    h.d = p.heap;
-    h.sm = nullptr;
-    h.nsm = 0;
-    h.len = 0;
+    cs_heap_init(h, nullptr, 0, p.heap);
     uint32_t nv = 0, ne = 0;
     p.agg[p.src] = 0.0f;
     p.flags[p.src] = 2;
@@ -92,10 +89,7 @@ __global__ void cs_k_tree_segment(CsTreeParams p) {
 __global__ void cs_k_tree_angular(CsTreeParams p) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     CsHeap h;
-    h.d = p.heap;
-    h.sm = nullptr;
-    h.nsm = 0;
-    h.len = 0;
+    cs_heap_init(h, nullptr, 0, p.heap);
     uint32_t nv = 0;
     p.order[nv++] = p.src;
     p.reached[p.src] = 1;

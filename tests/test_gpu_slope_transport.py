@@ -200,3 +200,24 @@ def test_overflow_then_retry_segment(oracle_mod):
     res = ns.segment_centrality(distances=[60], pbar_disabled=True)
     ref, _ = oracle_mod.OracleGraph(ns.frozen()).segment_centrality(d, b, s, H.SPEED, n_threads=8)
     np.testing.assert_allclose(res._out, ref, rtol=RTOL, atol=1e-6)
+
+
+def test_reach_capacity_grows_automatically(oracle_mod):
+    """The arena starts at 16 384 reached nodes per source; a call that needs more is repeated with a larger arena
+    (the reference has no such limit: its 20 km Greater-London runs reach 69 k nodes)."""
+    ns, _ = synth.config("cfg4", scale=0.3)
+    set_kernel(1)
+    f = ns.frozen()
+    centre = np.array([f.xs.mean(), f.ys.mean()])
+    src = np.sort(np.argsort(np.hypot(f.xs - centre[0], f.ys - centre[1]))[:6]).astype(np.uint32)
+    d, b, s = H.pair(distances=[3500])
+    res = ns.centrality_shortest(distances=[3500], source_indices=src.tolist(), sample_probability=1.0, pbar_disabled=True)
+    assert res.stats["kernel_used"] == 1
+    assert res.stats["settled"] / len(src) > 16384 and res.stats["reach_capacity"] > 16384
+    elig = np.zeros(f.node_bound, np.uint8)
+    elig[src] = 1
+    ref, cnt = oracle_mod.OracleGraph(f).centrality_shortest(d, b, s, H.SPEED, sources=src, wt=np.ones(len(src), np.float32),
+                                                             eligible=elig, n_threads=6)  # fmt: skip
+    assert np.array_equal(res._out[0], ref[0]) and np.array_equal(res._out[2], ref[2])
+    np.testing.assert_allclose(res._out, ref, rtol=RTOL, atol=1e-7)
+    assert res.stats["settled"] == cnt["settled"]
