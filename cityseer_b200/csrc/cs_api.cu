@@ -13,6 +13,7 @@
 #include "cs_shortest.cuh"
 #include "cs_shortest3.cuh"
 #include "cs_segment.cuh"
+#include "cs_segment3.cuh"
 #include "cs_simplest.cuh"
 #include "cs_tree.cuh"
 
@@ -90,7 +91,13 @@ struct cs_graph {
     size_t v3_ncsec = 0;
     uint2* d3_jinfo = nullptr;
     uint4 *d3_links = nullptr, *d3_ctab = nullptr;
-    float *d3_cnum = nullptr, *d3_csec = nullptr, *d3_weight = nullptr;
+    float *d3_cnum = nullptr, *d3_csec = nullptr, *d3_weight = nullptr, *d3_clen = nullptr, *d3_cimp = nullptr;
+    bool v3_loops = false;  // the graph has self-loops (not part of the contracted copy)
+    // small node-level arena of the segment heap-order replay when the chain kernel serves the call
+    uint8_t* d_arena2 = nullptr;
+    CsArenaLayout lay2{};
+    uint32_t workers2 = 0;
+    int arena2_D = 0;
     uint32_t *d3_int_chain = nullptr, *d3_orig_of_new = nullptr, *d3_new_of_orig = nullptr;
     uint8_t* d3_eligible = nullptr;
     float cached_speed3 = -1.f;
@@ -194,7 +201,7 @@ static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, c
                           const std::vector<uint32_t>& in_off, const std::vector<uint32_t>& out_off,
                           const std::vector<CsEdge>& in_rec, const std::vector<CsEdge>& out_rec,
                           const std::vector<float>& in_num, const std::vector<float>& out_num,
-                          const std::vector<float>& weight);
+                          const std::vector<float>& in_imp, const std::vector<float>& weight);
 
 extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_exists, const uint8_t* live,
                                      const float* weight, const double* xs, const double* ys, const double* z,
@@ -420,7 +427,7 @@ extern "C" cs_graph* cs_graph_create(uint32_t node_bound, const uint8_t* node_ex
         rc |= upload(&g->d_ang_rec, ang_rec);
         rc |= upload(&g->d_ang_num, ang_num);
     }
-    if (!rc) rc = build_v3_graph(g, n, node_exists, xs, ys, in_off, out_off, in_rec, out_rec, in_num, out_num, w);
+    if (!rc) rc = build_v3_graph(g, n, node_exists, xs, ys, in_off, out_off, in_rec, out_rec, in_num, out_num, in_imp, w);
     if (rc) {
         delete g;
         return nullptr;
@@ -448,7 +455,8 @@ extern "C" void cs_graph_destroy(cs_graph* g) {
                     (void*)g->d_error, (void*)g->d_out, (void*)g->d_arena, (void*)g->d_acc, (void*)g->d3_jinfo,
                     (void*)g->d3_links, (void*)g->d3_ctab, (void*)g->d3_cnum, (void*)g->d3_csec, (void*)g->d3_weight,
                     (void*)g->d3_int_chain, (void*)g->d3_orig_of_new, (void*)g->d3_new_of_orig, (void*)g->d3_eligible,
-                    (void*)g->d_od_off, (void*)g->d_od_dst, (void*)g->d_od_w, (void*)g->d_redo})
+                    (void*)g->d_od_off, (void*)g->d_od_dst, (void*)g->d_od_w, (void*)g->d_redo, (void*)g->d3_clen,
+                    (void*)g->d3_cimp, (void*)g->d_arena2})
         if (p) cudaFree(p);
     if (g->h_progress) cudaFreeHost(g->h_progress);
     for (auto& e : g->ev)
@@ -1109,4 +1117,5 @@ extern "C" int cs_shortest_search(cs_graph* g, uint32_t src, uint32_t max_second
 
 // ------------------------------------------------------------------------------------------------ segment / simplest
 #include "cs_api_more.inl"
+#include "cs_api_seg3.inl"
 #include "cs_api_tree.inl"

@@ -96,6 +96,10 @@ extern "C" int cs_dijkstra_tree_shortest(cs_graph* g, uint32_t src, uint32_t max
 }
 
 // ------------------------------------------------------------------------------------------------ segment
+static int run_segment3(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
+                        float speed_m_s, int compute_closeness, int compute_betweenness, uint64_t n_sources,
+                        const uint32_t* sources, double* out, int out_on_device, int accumulate, cs_stats* stats);
+
 static int run_segment(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
                        float speed_m_s, int compute_closeness, int compute_betweenness, uint64_t n_sources,
                        const uint32_t* sources, double* out, int out_on_device, int accumulate, cs_stats* stats) {
@@ -195,10 +199,17 @@ extern "C" int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distanc
                                      float speed_m_s, int compute_closeness, int compute_betweenness, uint64_t n_sources,
                                      const uint32_t* sources, double* out, int out_on_device, int accumulate, cs_stats* stats) {
     for (;;) {
-        const int rc = run_segment(g, D, distances, betas, seconds, speed_m_s, compute_closeness, compute_betweenness,
-                                   n_sources, sources, out, out_on_device, accumulate, stats);
+        // the chain-contracted kernel serves graphs that are mostly chain interiors (decomposed / OSM-like street networks)
+        const bool chain = g && out && g->v3_ok && !g->v3_loops && !g->twin_missing && n_sources > 0 && D >= 1 &&
+                           D <= CS_MAX_THRESHOLDS && seconds && (compute_closeness || compute_betweenness) && speed_m_s > 0.f &&
+                           std::isfinite(speed_m_s) && (g->opt_kernel == 3 || (g->opt_kernel == 0 && g->v3_I >= g->v3_J));
+        const int rc = chain ? run_segment3(g, D, distances, betas, seconds, speed_m_s, compute_closeness,
+                                            compute_betweenness, n_sources, sources, out, out_on_device, accumulate, stats)
+                             : run_segment(g, D, distances, betas, seconds, speed_m_s, compute_closeness,
+                                           compute_betweenness, n_sources, sources, out, out_on_device, accumulate, stats);
         // the segment kernel adds straight into `out`: a failed attempt can only be repeated when it started from zero
-        if (!rc || accumulate || !g || !grow_after_overflow(g, g->n, g->lay.rcap)) return rc;
+        if (!rc || accumulate || !g) return rc;
+        if (!grow_after_overflow(g, chain ? (size_t)g->v3_J + 1 : (size_t)g->n, g->lay.rcap)) return rc;
     }
 }
 

@@ -42,7 +42,7 @@ static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, c
                           const std::vector<uint32_t>& in_off, const std::vector<uint32_t>& out_off,
                           const std::vector<CsEdge>& in_rec, const std::vector<CsEdge>& out_rec,
                           const std::vector<float>& in_num, const std::vector<float>& out_num,
-                          const std::vector<float>& weight) {
+                          const std::vector<float>& in_imp, const std::vector<float>& weight) {
     g->v3_ok = false;
     const float MIN_NUM = 0.05f;  // shorter pieces are never contracted (f32 walks must stay strictly increasing; the kernel checks)
     // ---- every non-loop in-edge needs a mutual twin
@@ -154,7 +154,10 @@ static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, c
         const uint32_t v = junctions[q];
         uint32_t c = 0;
         for (uint32_t j = 0; j < in_off[v + 1] - in_off[v]; ++j) {
-            if (in_rec[in_off[v] + j].meta & 0x200u) continue;
+            if (in_rec[in_off[v] + j].meta & 0x200u) {
+                g->v3_loops = true;  // self-loops are visited edges of segment_centrality: served by the node-level kernel
+                continue;
+            }
             if (c >= CS3_MAX_LINKS) return 0;
             link_idx[in_off[v] + j] = (uint8_t)c++;
         }
@@ -255,6 +258,15 @@ static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, c
     const uint32_t C = NC + (uint32_t)directs.size();
     std::vector<uint32_t> soff(C, 0);
     std::vector<float> cnum;
+    // segment_centrality reads, per visited piece, the length and impedance of the edge LEAVING the visiting node
+    // (get_edge_length_unchecked(start = popped node, end = neighbour), centrality.rs:2234-2243): same block layout as the
+    // seconds - entry t of the fwd array belongs to the piece the A -> B wave crosses in step t, visited from m_t
+    std::vector<float> clen, cimp;
+    auto in_slot_from = [&](uint32_t at, uint32_t from) -> uint32_t {  // in-list slot (absolute) of the edge from -> at
+        for (uint32_t s2 = in_off[at]; s2 < in_off[at + 1]; ++s2)
+            if (in_rec[s2].nbr == from) return s2;
+        return in_off[at];
+    };
     auto in_num_from = [&](uint32_t at, uint32_t from) -> float {  // numerator of the edge from -> at (at interior)
         return in_rec[in_off[at]].nbr == from ? in_num[in_off[at]] : in_num[in_off[at] + 1];
     };
@@ -278,18 +290,44 @@ static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, c
                 bwd[t] = out_num_to(node(k), node(k + 1));
             }
         }
-        for (uint32_t t = 0; t <= k; ++t) cnum.push_back(fwd[t]);
+        clen.resize(cnum.size(), 0.f);
+        cimp.resize(cnum.size(), 1.f);
+        for (uint32_t t = 0; t <= k; ++t) {
+            cnum.push_back(fwd[t]);
+            // the wave from A crosses piece t from m_t: the edge m_t -> m_{t+1} is the twin of the in-edge m_{t+1} -> m_t
+            const uint32_t s2 = in_slot_from(node(t), node(t + 1));
+            clen.push_back(in_rec[s2].aux);
+            cimp.push_back(in_imp[s2]);
+        }
         while (cnum.size() & 3u) cnum.push_back(0.f);  // bwdr starts at cs3_pb(k): both arrays 16-byte aligned
-        for (uint32_t t = 0; t <= k; ++t) cnum.push_back(bwd[k - t]);
+        clen.resize(cnum.size(), 0.f);
+        cimp.resize(cnum.size(), 1.f);
+        for (uint32_t t = 0; t <= k; ++t) {
+            cnum.push_back(bwd[k - t]);
+            // the wave from B crosses piece k - t from m_{k+1-t}: the edge m_{k+1-t} -> m_{k-t}
+            const uint32_t s2 = in_slot_from(node(k + 1 - t), node(k - t));
+            clen.push_back(in_rec[s2].aux);
+            cimp.push_back(in_imp[s2]);
+        }
     }
     for (uint32_t d = 0; d < directs.size(); ++d) {
         while (cnum.size() & 3u) cnum.push_back(0.f);
         soff[NC + d] = (uint32_t)cnum.size();
+        clen.resize(cnum.size(), 0.f);
+        cimp.resize(cnum.size(), 1.f);
         cnum.push_back(in_num[directs[d].slotA]);  // B -> A: A's outward step
+        clen.push_back(in_rec[directs[d].slotA].aux);
+        cimp.push_back(in_imp[directs[d].slotA]);
         while (cnum.size() & 3u) cnum.push_back(0.f);
+        clen.resize(cnum.size(), 0.f);
+        cimp.resize(cnum.size(), 1.f);
         cnum.push_back(in_num[directs[d].slotB]);  // A -> B: B's outward step (at cs3_pb(0))
+        clen.push_back(in_rec[directs[d].slotB].aux);
+        cimp.push_back(in_imp[directs[d].slotB]);
     }
     while (cnum.size() & 3u) cnum.push_back(0.f);
+    clen.resize(cnum.size(), 0.f);
+    cimp.resize(cnum.size(), 1.f);
     // ---- link records by new junction id
     std::vector<uint32_t> jn_off(J + 1, 0);
     for (uint32_t q = 0; q < J; ++q) jn_off[q + 1] = jn_off[q] + nlinks[jorder[q]];
@@ -343,6 +381,8 @@ static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, c
     rc |= upload(&g->d3_links, links);
     rc |= upload(&g->d3_cnum, cnum);
     rc |= upload(&g->d3_csec, cnum);
+    rc |= upload(&g->d3_clen, clen);
+    rc |= upload(&g->d3_cimp, cimp);
     rc |= upload(&g->d3_ctab, ctab);
     rc |= upload(&g->d3_int_chain, int_chain);
     rc |= upload(&g->d3_orig_of_new, orig_of_new);

@@ -40,6 +40,9 @@ struct CsSegmentParams {
     // sources a CTA takes per round (1 .. CS_SEG_WARPS; warps beyond it idle at the barriers): a short replay list is
     // spread over all SMs instead of filling a few CTAs with 32 serial heap replays each
     uint32_t src_per_cta;
+    // arena slots are indexed blockIdx.x * src_per_cta + warp instead of blockIdx.x * CS_SEG_WARPS + warp: the replay
+    // launch behind the chain-contracted kernel runs in a small arena of its own
+    int compact_arena;
 };
 
 // The heap of the replay (cs_heap.cuh): the first CS_SEG_HEAP_SMEM entries in the warp's shared-memory bins, the arena
@@ -136,7 +139,8 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
     __shared__ int s_err;
     const uint32_t lane = cs_lane();
     const uint32_t wic = threadIdx.x >> 5;
-    const uint32_t worker = blockIdx.x * CS_SEG_WARPS + wic;
+    const uint32_t worker = p.compact_arena ? blockIdx.x * p.src_per_cta + (wic < p.src_per_cta ? wic : 0u)
+                                            : blockIdx.x * CS_SEG_WARPS + wic;
     uint32_t* bins = s_bins_all + (size_t)wic * CS_NBINS;
     const CsWarpArena A = cs_arena(p.arena, p.lay, worker);
     float2* seglen = reinterpret_cast<float2*>(A.sigma);  // per rank {origin segment length (-1 = pending), last segment length}

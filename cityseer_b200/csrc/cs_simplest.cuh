@@ -51,13 +51,15 @@ __global__ void cs_k_init_ang(uint8_t* arena, size_t stride, size_t ds_off, size
     for (size_t k = i; k < n_nodes; k += step) dn[k] = make_uint2(CS_INF_BITS, CS_INF_BITS);
 }
 
-// resident CTAs per SM: the replayed heap leaves one lane busy for long stretches, so warps are what hides latency
-// (measured on cfg3: 3 CTAs 341 k sources/s, 4: 385 k, 5: 403 k, 6: 406 k, 8: 404 k)
+// Resident CTAs per SM.  With the heap in shared memory the kernel is bound by the latency of its per-warp arena traffic
+// (the arenas of all resident warps exceed the L2: ~3.9 MB of DRAM traffic per source, profiles/r02*), and more warps
+// only enlarge that working set.  Measured on cfg #3 (bench, heap entries in shared memory / CTAs per SM): 512/3 319 k
+// sources/s, 512/4 357 k, 512/5 329 k, 512/6 318 k, 256/5 336 k, 256/6 358 k, 256/8 358 k.
 #ifndef CS_ANG_MIN_BLOCKS
-#define CS_ANG_MIN_BLOCKS 5
+#define CS_ANG_MIN_BLOCKS 4
 #endif
 #ifndef CS_ANG_HEAP_SMEM
-#define CS_ANG_HEAP_SMEM 512  // heap entries per warp kept in shared memory (4 KB; 5 CTAs x 8 warps = 160 KB per SM)
+#define CS_ANG_HEAP_SMEM 512  // heap entries per warp kept in shared memory (4 KB; 4 CTAs x 8 warps = 128 KB per SM)
 #endif
 template <int DT>
 __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_ANG_MIN_BLOCKS) cs_k_simplest(const CsSimplestParams p) {

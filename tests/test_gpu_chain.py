@@ -263,3 +263,77 @@ def test_full_size_cfg4_source_sample_vs_oracle(oracle_mod):
     for m, name in enumerate(("density", "harmonic", "beta", "betweenness")):
         np.testing.assert_allclose(got[m], ref[m], rtol=RTOL, atol=1e-6, err_msg=name)
     assert st["settled"] == cnt["settled"] and st["edge_iters"] == cnt["edge_iters"]
+
+
+# ------------------------------------------------------------------------------------------------ segment_centrality
+# The chain-contracted segment kernel (cs_segment3.cuh) on the same shapes, against the CPU oracle.  Sources whose tree
+# has exactly tied parents are set aside by the kernel and replayed in heap order by the node-level kernel; the counters
+# of both launches add up to the oracle's.
+def check_segment(oracle_mod, ns, distances, **kw):
+    d, b, s = H.pair(distances=distances)
+    res = ns.segment_centrality(distances=distances, pbar_disabled=True, **kw)
+    assert res.stats["kernel_used"] == 3
+    ref, cnt = oracle_mod.OracleGraph(ns.frozen()).segment_centrality(
+        d, b, s, H.SPEED, closeness=kw.get("compute_closeness", True), betweenness=kw.get("compute_betweenness", True), n_threads=8)  # fmt: skip
+    for m, name in enumerate(("density", "harmonic", "beta", "betweenness")):
+        np.testing.assert_allclose(res._out[m], ref[m], rtol=RTOL, atol=1e-6, err_msg=name)
+    assert res.stats["settled"] == cnt["settled"] and res.stats["edge_iters"] == cnt["edge_iters"]
+    return res
+
+
+def test_segment_long_path_and_ring(oracle_mod):
+    check_segment(oracle_mod, build([[(0, 0), (1500, 0)]]), [200, 600, 1200])
+    c = [(300 * np.cos(t), 300 * np.sin(t)) for t in np.linspace(0, 2 * np.pi, 13)[:-1]]
+    check_segment(oracle_mod, build([c + [c[0]]]), [300, 700, 1500])
+
+
+def test_segment_loop_chain_on_a_stem(oracle_mod):
+    ring = [(400 + 150 * np.cos(t), 150 * np.sin(t)) for t in np.linspace(np.pi, 3 * np.pi, 10)]
+    check_segment(oracle_mod, build([[(0, 0), (250, 0)], ring]), [150, 400, 900])
+
+
+def test_segment_parallel_and_symmetric_chains(oracle_mod):
+    a, b = (0.0, 0.0), (600.0, 0.0)
+    ns = build([[a, (300, 40), b], [a, (300, -40.3), b], [a, (300, 120), b], [(-200, 0), a], [b, (800, 0)]])
+    check_segment(oracle_mod, ns, [300, 600, 1200])
+    a, b = (0.0, 0.0), (500.0, 0.0)
+    ns = build([[a, (100, 80), (400, 80), b], [a, (100, -80), (400, -80), b], [(-150, 0), a], [b, (650, 0)]], step=25.0)
+    check_segment(oracle_mod, ns, [250, 500, 1000])
+
+
+@pytest.mark.parametrize("distances", [[700], [400, 800, 1600], [200, 400, 600, 800, 1000]])
+def test_segment_decomposed_grid(oracle_mod, distances):
+    ns, _ = synth.config("cfg4", 0.05)
+    res = check_segment(oracle_mod, ns, distances)
+    assert res.stats["fallback_sources"] < 0.05 * res.stats["sources"]  # jittered grid: exact ties are rare
+
+
+@pytest.mark.parametrize("flags", [(True, False), (False, True)])
+def test_segment_flag_combinations_and_slope(oracle_mod, flags):
+    ns, _ = synth.config("cfg4", 0.05, hilly=True)
+    check_segment(oracle_mod, ns, [300, 900], compute_closeness=flags[0], compute_betweenness=flags[1])
+
+
+def test_segment_regular_grid_is_replayed_in_heap_order(oracle_mod):
+    # equal pieces everywhere: nearly every source has exactly tied parents and goes through the heap-order replay
+    gx, gy = np.meshgrid(np.arange(10), np.arange(10), indexing="xy")
+    xy = np.stack([gx.ravel() * 100.0, gy.ravel() * 100.0], axis=1)
+    idx = np.arange(100).reshape(10, 10)
+    e = np.concatenate([np.stack([idx[:, :-1].ravel(), idx[:, 1:].ravel()], 1), np.stack([idx[:-1, :].ravel(), idx[1:, :].ravel()], 1)])
+    xy2, e2 = synth.decompose(xy, e, 20.0)
+    ns = synth.primal_network(xy2, e2)
+    res = check_segment(oracle_mod, ns, [200, 400, 800])
+    assert res.stats["fallback_sources"] > 0.5 * res.stats["sources"]
+
+
+def test_segment_kernels_agree_on_the_sampled_full_size_graph(oracle_mod):
+    # the node-level kernel on the same graph and sources as the chain kernel (both are compared with the oracle in
+    # test_full_size_cfg4_source_sample_vs_oracle / tests/test_gpu_segment.py; this pins them against each other)
+    ns, _ = synth.config("cfg4", 0.12)
+    a = ns.segment_centrality(distances=[400, 800, 1600], pbar_disabled=True)
+    assert a.stats["kernel_used"] == 3
+    ns.device_graph().set_option("kernel", 1)
+    b = ns.segment_centrality(distances=[400, 800, 1600], pbar_disabled=True)
+    assert b.stats["kernel_used"] != 3
+    np.testing.assert_allclose(a._out, b._out, rtol=1e-9, atol=1e-9)
+    assert a.stats["settled"] == b.stats["settled"] and a.stats["sum_ci"] == b.stats["sum_ci"]
