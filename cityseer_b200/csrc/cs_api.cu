@@ -542,10 +542,11 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
     rcap = std::max(rcap, 32u);
     const uint32_t qcap = rcap * 2 + 64;
     uint32_t workers = g->cfg_workers ? g->cfg_workers
-                                      : (uint32_t)g->sm_count * (kind == 3   ? CS3_WORKERS_PER_SM
+                                      : (uint32_t)g->sm_count * (kind == 3   ? std::max<uint32_t>(CS3_WORKERS_PER_SM, CS3S_WARPS)
                                                                  : kind == 1 ? CS_SEG_MIN_BLOCKS * CS_SEG_WARPS
                                                                              : CS_MIN_BLOCKS * CS_WARPS_PER_CTA);
-    const uint32_t gran = kind == 3 ? CS3_WORKERS_PER_SM : kind == 1 ? CS_SEG_WARPS : CS_WARPS_PER_CTA;  // warps of the widest CTA that uses the arena
+    // warps of the widest CTA that uses the arena (kind 3 serves both chain kernels)
+    const uint32_t gran = kind == 3 ? std::max<uint32_t>(CS3_WORKERS_PER_SM, CS3S_WARPS) : kind == 1 ? CS_SEG_WARPS : CS_WARPS_PER_CTA;
     workers = std::max<uint32_t>(gran, workers / gran * gran);
     CsArenaLayout L{};
     size_t off = 0;

@@ -5,9 +5,11 @@ static cudaError_t seg3_launch_t(const CsSegment3Params& t, uint32_t workers, cu
     constexpr uint32_t smem = cs3s_smem_bytes<DT>();
     cudaError_t e = cudaFuncSetAttribute(cs_k_segment3<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(workers / CS3S_WARPS, (t.n_sources + CS3S_WARPS - 1) / CS3S_WARPS);
+    constexpr uint32_t W = cs3s_warps<DT>();
+    static_assert(smem <= 227 * 1024, "the CTA must fit the SM's shared memory");
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(workers / W, (t.n_sources + W - 1) / W);
     if (grid == 0) return cudaSuccess;
-    cs_k_segment3<DT><<<grid, CS3S_WARPS * 32, smem, st>>>(t);
+    cs_k_segment3<DT><<<grid, W * 32, smem, st>>>(t);
     return cudaGetLastError();
 }
 static cudaError_t seg3_launch(const CsSegment3Params& t, uint32_t workers, cudaStream_t st) {

@@ -18,9 +18,15 @@
 #include "cs_segment.cuh"
 #include "cs_shortest3.cuh"
 
+// CTA shape: one phase-synchronous CTA per SM like the other chain kernel, but this one is bound by the arithmetic of the
+// integrals (logf and two libm-exact expf per piece side and threshold), not by dependent loads: resident warps pay even at
+// the price of register spills.  Measured on cfg #4 (400/800/1600 m): 16 warps (128 registers) 1.26 M sources/s, 20 (96)
+// 1.30 M, 24 (80) 1.36 M, 28 (72) 1.38 M.  Shared memory per warp grows with the threshold count (outflow accumulators).
 #ifndef CS3S_WARPS
-#define CS3S_WARPS 16
+#define CS3S_WARPS 28  // up to four thresholds; the widest shape decides the arena's worker count
 #endif
+template <int DT>
+__host__ __device__ constexpr uint32_t cs3s_warps() { return DT <= 4 ? CS3S_WARPS : DT <= 8 ? 24u : 20u; }
 #define CS3S_NBP 128u  // staged pieces per closeness sub-iteration (12-byte records in the 2 KB region A)
 
 struct CsSegment3Params {
@@ -72,8 +78,8 @@ __device__ __forceinline__ void cs3s_auc(const CsSegment3Params& p, float sd, fl
 }
 
 template <int DT>
-__global__ void __launch_bounds__(CS3S_WARPS * 32, 1) cs_k_segment3(const CsSegment3Params p) {
-    constexpr uint32_t WARPS = CS3S_WARPS;
+__global__ void __launch_bounds__(cs3s_warps<DT>() * 32, 1) cs_k_segment3(const CsSegment3Params p) {
+    constexpr uint32_t WARPS = cs3s_warps<DT>();
     constexpr uint32_t NB = cs3s_nb<DT>();  // staged nodes per sub-iteration of the subtree pass
     // per-warp shared memory: region A (2 KB): P1 task table | P2 bins | S3 piece records | S5 node ids, costs, lengths;
     // region B (4 KB): S3 chain-block cells | S5 credits (f64) and own terms (f32); region C: link lists, link bytes, outflow
@@ -890,5 +896,5 @@ __global__ void cs_k_epilogue_segment3(const double* __restrict__ acc_b, double*
 
 template <int DT>
 static constexpr uint32_t cs3s_smem_bytes() {
-    return CS3S_WARPS * (CS3_NBINS * 4 + 8 * 32 * 16 + DT * 32 * 8 + 512 + 256 + 256);
+    return cs3s_warps<DT>() * (CS3_NBINS * 4 + 8 * 32 * 16 + DT * 32 * 8 + 512 + 256 + 256);
 }

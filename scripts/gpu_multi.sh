@@ -10,4 +10,5 @@ for fn in shortest segment simplest; do
   timeout 600 $TR --master-port $p bench.py --gpus $N --function $fn --steps 5 --warmup 3 > gpurun_out/${tag}_bench_${fn}_${N}gpu.json 2> gpurun_out/${tag}_bench_${fn}_${N}gpu.err
   tail -c 600 gpurun_out/${tag}_bench_${fn}_${N}gpu.json | head -c 300; echo
 done
+timeout 300 python -m pytest tests/test_gpu_sharded.py -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/${tag}_pytest_sharded.log 2>&1; tail -2 gpurun_out/${tag}_pytest_sharded.log
 timeout 900 $TR --master-port 29720 scripts/cfg5_sharded.py --km 5 10 > gpurun_out/${tag}_cfg5_${N}gpu.log 2>&1; grep workload gpurun_out/${tag}_cfg5_${N}gpu.log
