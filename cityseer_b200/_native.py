@@ -93,6 +93,10 @@ SIGNATURES = {
     "cs_dijkstra_tree_shortest": (
         C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, _u32p, _u32p, C.POINTER(C.c_int64), _f32p],
     ),
+    "cs_dijkstra_trees_shortest": (
+        C.c_int,
+        [C.c_void_p, C.c_uint64, _u32p, C.c_uint32, C.c_float, C.c_uint32, _u32p, _u32p, C.POINTER(C.c_int64), _f32p],
+    ),
     "cs_dijkstra_tree_segment": (
         C.c_int,
         [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, _u32p, _u32p, _u64p, _u32p, C.POINTER(C.c_int64), _f32p,
@@ -390,6 +394,22 @@ class DeviceGraph:
             if rc:
                 raise ValueError(_err(self._lib))
         return agg, sig, npred
+
+    def dijkstra_trees_shortest(self, sources: np.ndarray, max_seconds: int, speed: float, capacity: int):
+        """Batched dijkstra_tree_shortest: (counts [n], visited_order [n, cap], pred [n, cap] (-1 none), seconds [n, cap])."""
+        sources = np.ascontiguousarray(sources, np.uint32)
+        n = len(sources)
+        counts = np.zeros(max(n, 1), np.uint32)
+        order = np.zeros((max(n, 1), capacity), np.uint32)
+        pred = np.full((max(n, 1), capacity), -1, np.int64)
+        agg = np.full((max(n, 1), capacity), np.inf, np.float32)
+        with self._call_lock:
+            rc = self._lib.cs_dijkstra_trees_shortest(self._h, n, _ptr(sources, _u32p), int(max_seconds), float(speed),
+                                                      int(capacity), _ptr(counts, _u32p), _ptr(order, _u32p),
+                                                      pred.ctypes.data_as(C.POINTER(C.c_int64)), _ptr(agg, _f32p))  # fmt: skip
+            if rc:
+                raise ValueError(_err(self._lib))
+        return counts[:n], order[:n], pred[:n], agg[:n]
 
     def dijkstra_tree(self, kind: int, src_idx: int, max_seconds: int, speed: float):
         """Single-source tree dumps.  kind 0 = dijkstra_tree_shortest: (visited order, pred per node (-1 none), seconds

@@ -95,6 +95,102 @@ extern "C" int cs_dijkstra_tree_shortest(cs_graph* g, uint32_t src, uint32_t max
     return rc;
 }
 
+// Batched dijkstra_tree_shortest (the searches that feed the reference's data.rs aggregations run
+// one source at a time, centrality.rs:1141-1200): many sources per launch, one warp each, every search replayed in the
+// reference's heap order so that visit order and predecessors are exact under ties.  Outputs are [n_sources][capacity].
+extern "C" int cs_dijkstra_trees_shortest(cs_graph* g, uint64_t n_sources, const uint32_t* sources, uint32_t max_seconds,
+                                          float speed_m_s, uint32_t capacity, uint32_t* counts, uint32_t* visited_order,
+                                          int64_t* pred, float* agg_seconds) {
+    if (!g) return cs_fail("null graph");
+    if (!sources || !counts || !visited_order || !pred || !agg_seconds) return cs_fail("null argument");
+    if (capacity == 0) return cs_fail("capacity must be positive");
+    if (!(speed_m_s > 0.f) || !std::isfinite(speed_m_s)) return cs_fail("speed_m_s must be finite and positive, got %f", speed_m_s);
+    for (uint64_t i = 0; i < n_sources; ++i)
+        if (sources[i] >= g->n) return cs_fail("src_idx %u out of range for network with node_bound %u", sources[i], g->n);
+    if (n_sources == 0) return 0;
+    CS_CUDA(cudaSetDevice(g->device));
+    for (;;) {
+        g->last_kernel = 0;
+        if (ensure_arena(g, 1, 1)) return 1;
+        uint32_t launches = 0;
+        if (stage_sources(g, n_sources, sources, nullptr, nullptr)) return 1;
+        if (prep_seconds(g, speed_m_s, false, &launches)) return 1;
+        CS_CUDA(cudaMemsetAsync(g->d_counters, 0, CS_NCOUNTERS * sizeof(unsigned long long), g->stream));
+        CS_CUDA(cudaMemsetAsync(g->d_error, 0, sizeof(int), g->stream));
+        const size_t total = (size_t)n_sources * capacity;
+        uint32_t *d_order = nullptr, *d_pred = nullptr, *d_count = nullptr;
+        float* d_agg = nullptr;
+        CS_CUDA(cudaMalloc(&d_order, total * 4));
+        CS_CUDA(cudaMalloc(&d_pred, total * 4));
+        CS_CUDA(cudaMalloc(&d_agg, total * 4));
+        CS_CUDA(cudaMalloc(&d_count, n_sources * 4));
+        CS_CUDA(cudaMemsetAsync(d_count, 0, n_sources * 4, g->stream));
+        CsSegmentParams p{};
+        p.g = graph_dev(g);
+        p.D = 1;
+        p.max_seconds = (float)max_seconds;
+        p.speed = speed_m_s;
+        p.sources = g->d_sources;
+        p.n_sources = n_sources;
+        p.counters = g->d_counters;
+        p.error = g->d_error;
+        p.arena = g->d_arena;
+        p.lay = g->lay;
+        p.delta = default_delta(g, speed_m_s);
+        p.bin_scale = (float)CS_NBINS / (((float)max_seconds + 1.0f) * ((float)max_seconds + 1.0f));
+        p.replay = 1;
+        p.batch_cap = capacity;
+        p.b_order = d_order;
+        p.b_pred = d_pred;
+        p.b_agg = d_agg;
+        p.b_count = d_count;
+        int rc = 0;
+        if (segment_smem_optin(g)) rc = 1;
+        if (!rc) {
+            const uint32_t ctas = g->workers / CS_SEG_WARPS;
+            p.src_per_cta = (uint32_t)std::min<uint64_t>(CS_SEG_WARPS, (n_sources + ctas - 1) / ctas);
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(ctas, (n_sources + p.src_per_cta - 1) / p.src_per_cta);
+            cs_k_segment<1><<<grid, CS_SEG_WARPS * 32, CS_SEG_SMEM_BYTES, g->stream>>>(p);
+            if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(g->stream) != cudaSuccess)
+                rc = cs_fail("CUDA error in the batched tree search");
+        }
+        int herr = 0;
+        if (!rc) {
+            cudaMemcpy(&herr, g->d_error, sizeof(int), cudaMemcpyDeviceToHost);
+            g->last_herr = herr;
+            if (herr) {
+                g->arena_kind = -1;
+                rc = cs_fail("search arena overflow: a source reached more than %u nodes; raise reach_capacity via cs_graph_configure", g->lay.rcap);
+            }
+        }
+        if (!rc) {
+            cudaMemcpy(counts, d_count, n_sources * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(visited_order, d_order, total * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(agg_seconds, d_agg, total * 4, cudaMemcpyDeviceToHost);
+            std::vector<uint32_t> hp(total);
+            cudaMemcpy(hp.data(), d_pred, total * 4, cudaMemcpyDeviceToHost);
+            for (uint64_t s2 = 0; s2 < n_sources; ++s2) {
+                const uint32_t c = std::min(counts[s2], capacity);
+                for (uint32_t k = 0; k < c; ++k) {
+                    const size_t at = (size_t)s2 * capacity + k;
+                    pred[at] = hp[at] == 0xffffffffu ? -1 : (int64_t)hp[at];
+                }
+            }
+        }
+        cudaFree(d_order);
+        cudaFree(d_pred);
+        cudaFree(d_agg);
+        cudaFree(d_count);
+        if (!rc) {
+            for (uint64_t s2 = 0; s2 < n_sources; ++s2)
+                if (counts[s2] > capacity)
+                    return cs_fail("source %u settled %u nodes, more than the output capacity %u", sources[s2], counts[s2], capacity);
+            return 0;
+        }
+        if (!grow_after_overflow(g, g->n, g->lay.rcap)) return rc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ segment
 static int run_segment3(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
                         float speed_m_s, int compute_closeness, int compute_betweenness, uint64_t n_sources,

@@ -31,6 +31,14 @@ struct CsSegmentParams {
     uint32_t* dump_pred;   // [n] predecessor node, 0xffffffff = none
     float* dump_agg;       // [n] seconds (prefilled with inf by the caller)
     uint32_t* dump_count;  // [1] number of settled nodes
+    // batched tree dumps (dijkstra_tree_shortest for many sources in one launch, replay == 1): source slot s owns entries
+    // [s * batch_cap, (s + 1) * batch_cap): settled node in pop order, its predecessor (0xffffffff = none), its seconds;
+    // b_count[s] = settled nodes (entries beyond batch_cap are dropped, the caller checks the count)
+    uint32_t batch_cap;
+    uint32_t* b_order;
+    uint32_t* b_pred;
+    float* b_agg;
+    uint32_t* b_count;
     // Equal-key settle order.  The single-predecessor rule (strict `<` in pop order, :1589) makes the tree depend on the
     // order in which the reference's BinaryHeap pops nodes whose seconds are bit-equal.  replay == 0: a source where two
     // tree parents with bit-equal seconds compete for a node is not accumulated but appended to redo_list; replay == 1:
@@ -234,6 +242,16 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
                 }
                 pred_rank = best_rank;
                 cs_st(&A.predmask[r], pred_rank == CS_NOSLOT ? 0u : (1u << best_j));
+                if (p.b_order) {
+                    const uint32_t idx = p.replay ? cs_ld(&popseq[r]) : r;
+                    if (idx < p.batch_cap) {
+                        const size_t at = (size_t)si * p.batch_cap + idx;
+                        p.b_order[at] = v;
+                        p.b_pred[at] = pred_rank == CS_NOSLOT ? 0xffffffffu : cs_ld(&A.s_node[pred_rank]);
+                        p.b_agg[at] = av;
+                    }
+                    if (r == 0) p.b_count[si] = R;
+                }
                 if (p.dump_order) {
                     p.dump_order[p.replay ? cs_ld(&popseq[r]) : r] = v;
                     p.dump_agg[v] = av;

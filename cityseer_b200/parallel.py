@@ -108,10 +108,20 @@ class _SharedHost:
 
                 torch.cuda.cudart().cudaHostUnregister(self._pinned_ptr)
                 self._pinned_ptr = None
-            self.array = None
+        except Exception:  # noqa: BLE001
+            pass
+        if self.owner:
+            try:
+                self.shm.unlink()  # the name goes away now; the pages live until the last mapping is closed
+            except Exception:  # noqa: BLE001
+                pass
+        self.array = None
+        try:
             self.shm.close()
-            if self.owner:
-                self.shm.unlink()
+        except BufferError:
+            # result arrays handed out earlier still view the mapping: leave it to process exit
+            self.shm._mmap = None  # noqa: SLF001
+            self.shm._buf = None  # noqa: SLF001
         except Exception:  # noqa: BLE001
             pass
 

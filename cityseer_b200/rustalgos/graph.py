@@ -187,7 +187,7 @@ class FrozenGraph:
     __slots__ = (
         "node_bound", "node_exists", "live", "weight", "z", "edge_bound", "edge_exists", "src", "dst", "edge_idx",
         "length", "angle_sum", "imp", "seconds", "shared_key", "stamp", "is_dual", "node_indices", "key_names",
-        "xs", "ys",
+        "xs", "ys", "_plan",
     )  # fmt: skip
 
 
@@ -710,7 +710,9 @@ class NetworkStructure:
         return out
 
     def _prepare_sources(self, sample_probability, sampling_weights, random_seed, source_indices):
-        """Returns (sources u32[], wt f32[], eligible u8[node_bound], n_visited_for_progress, is_sampled, scale)."""
+        """Returns (sources u32[], wt f32[], eligible u8[node_bound], n_visited_for_progress, is_sampled, scale)
+        — prepare_source_sampling / sample_source_weight of centrality.rs:1032-1139.  A handful of numpy passes: this runs
+        inside every timed call (a million-source plan costs a few milliseconds)."""
         f = self.frozen()
         nb = f.node_bound
         sw = None if sampling_weights is None else self._expand_sampling_weights(sampling_weights)
@@ -720,31 +722,49 @@ class NetworkStructure:
                 raise ValueError("sample_probability must be in (0.0, 1.0]")
         if source_indices is not None and sw is not None:
             raise ValueError("source_indices and sampling_weights are mutually exclusive")
-        node_indices = f.node_indices
+        cache = getattr(f, "_plan", None)
+        if cache is None:  # per frozen graph: live mask, live count, whether every slot holds a node
+            exists = f.node_exists.astype(bool)
+            live_mask = f.live.astype(bool) & exists
+            cache = {"live_mask": live_mask, "n_live": int(live_mask.sum()), "all_exist": bool(exists.all()),
+                     "live_u8": live_mask.astype(np.uint8), "node_indices_u32": f.node_indices.astype(np.uint32)}  # fmt: skip
+            try:
+                f._plan = cache
+            except AttributeError:
+                pass
+        n_live = cache["n_live"]
         if source_indices is not None:
-            src = np.asarray(source_indices if isinstance(source_indices, np.ndarray) else list(source_indices), dtype=np.int64)
-            bad = (src < 0) | (src >= nb)
-            if not bad.any():
-                bad = f.node_exists[src] == 0
-            if bad.any():
-                raise ValueError(f"node index {int(src[np.nonzero(bad)[0][0]])} does not exist in the graph")
-        live_mask = f.live.astype(bool) & f.node_exists.astype(bool)
-        n_live = int(live_mask[node_indices].sum())
-        eligible = np.zeros(nb, np.uint8)
-        is_indexed = source_indices is not None
-        if is_indexed:
-            sources_all = src
-            eligible[src] = 1
-        else:
-            sources_all = node_indices
-            eligible[live_mask] = 1
+            src = source_indices if isinstance(source_indices, np.ndarray) else np.asarray(list(source_indices), dtype=np.int64)
+            if src.dtype.kind not in "iu":
+                src = src.astype(np.int64)
+            if len(src):
+                lo, hi = int(src.min()), int(src.max())
+                if lo < 0 or hi >= nb:
+                    bad = src[(src < 0) | (src >= nb)]
+                    raise ValueError(f"node index {int(bad[0])} does not exist in the graph")
+                if not cache["all_exist"]:
+                    missing = f.node_exists[src] == 0
+                    if missing.any():
+                        raise ValueError(f"node index {int(src[np.nonzero(missing)[0][0]])} does not exist in the graph")
+            sources = np.ascontiguousarray(src, dtype=np.uint32)
+            eligible = np.zeros(nb, np.uint8)
+            eligible[sources] = 1
+            wt = f.weight[sources]
+            if sample_probability is not None and sample_probability != 1.0:
+                wt = (wt / np.float32(sample_probability)).astype(np.float32)
+            n_sources = len(sources)
+            scale = 1.0
+            if sample_probability is None:
+                scale = n_live / n_sources if n_sources else 1.0
+            return sources, np.ascontiguousarray(wt, dtype=np.float32), eligible, n_sources, True, scale
+        node_indices = f.node_indices
+        live_mask = cache["live_mask"]
+        eligible = cache["live_u8"].copy()
+        sources_all = node_indices
         n_sources = len(sources_all)
         wt_all = f.weight[sources_all].astype(np.float32)
-        keep = eligible[sources_all].astype(bool)
-        if is_indexed:
-            if sample_probability is not None:
-                wt_all = (wt_all / np.float32(sample_probability)).astype(np.float32)
-        elif sample_probability is not None:
+        keep = live_mask[sources_all]
+        if sample_probability is not None:
             # Bernoulli draw per node_bound slot. The reference draws from rand::StdRng (ChaCha12), whose stream is not
             # pinned by any upstream test (only same-seed self-consistency is); we use numpy's PCG64 — SURVEY.md §8c.
             rng = np.random.default_rng(random_seed)
@@ -753,16 +773,12 @@ class NetworkStructure:
             if sw is not None:
                 p = (p * sw).astype(np.float32)
             ps = p[sources_all]
-            keep &= (ps > 0.0) & (randoms[sources_all] < ps)
+            keep = keep & (ps > 0.0) & (randoms[sources_all] < ps)
             with np.errstate(divide="ignore", invalid="ignore"):
                 wt_all = (wt_all / ps).astype(np.float32)
         sources = np.ascontiguousarray(sources_all[keep], dtype=np.uint32)
         wt = np.ascontiguousarray(wt_all[keep], dtype=np.float32)
-        tracked = sample_probability is not None or is_indexed
-        scale = 1.0
-        if is_indexed and sample_probability is None:
-            scale = n_live / n_sources if n_sources else 1.0
-        return sources, wt, eligible, n_sources, tracked, scale
+        return sources, wt, eligible, n_sources, sample_probability is not None, 1.0
 
     # ------------------------------------------------------------------ compute entry points (CUDA only)
     def centrality_shortest(
@@ -970,6 +986,29 @@ class NetworkStructure:
             t.agg_seconds = float(agg[i])
             t.short_dist = float(short[i])
         return order.tolist(), tree_map
+
+    def dijkstra_trees_shortest(self, src_indices, max_seconds: int, speed_m_s: float, capacity: int | None = None):
+        """Extension: ``dijkstra_tree_shortest`` for many sources in one device launch — the call
+        shape of the reference's data-layer consumers (data.rs:520-602 run one tree search per data point).  Returns
+        ``(counts, visited_nodes, preds, agg_seconds)``: for source ``i`` the first ``counts[i]`` entries of row ``i`` are
+        the settled nodes in the reference's pop order, each node's tree predecessor (-1 for the source) and its travel
+        seconds (``short_dist = agg_seconds * speed_m_s``).  ``capacity`` bounds the nodes one source may settle."""
+        src = np.asarray(list(src_indices) if not isinstance(src_indices, np.ndarray) else src_indices, dtype=np.int64)
+        for i in src.tolist():
+            self._validate_dijkstra_inputs(int(i), float(speed_m_s))
+        speed = np.float32(speed_m_s)
+        dev = self.device_graph()
+        cap = int(capacity) if capacity else min(self.node_bound(), 16384)
+        while True:
+            try:
+                counts, order, pred, agg = dev.dijkstra_trees_shortest(src.astype(np.uint32), int(max_seconds), float(speed), cap)
+                break
+            except ValueError as e:
+                if capacity or "output capacity" not in str(e) or cap >= self.node_bound():
+                    raise
+                cap = min(self.node_bound(), cap * 4)
+        width = int(counts.max()) if len(counts) else 0
+        return counts, order[:, :width], pred[:, :width], agg[:, :width]
 
     def dijkstra_tree_simplest(self, src_idx: int, max_seconds: int, speed_m_s: float):
         """centrality.rs:1510-1521"""

@@ -145,6 +145,16 @@ int cs_betweenness_od_shortest(cs_graph* g, int D, const uint32_t* distances, co
 int cs_dijkstra_tree_shortest(cs_graph* g, uint32_t src, uint32_t max_seconds, float speed_m_s, uint32_t* n_visited,
                               uint32_t* visited_order, int64_t* pred, float* agg_seconds);
 
+/* Batched form of cs_dijkstra_tree_shortest: the searches that feed the reference's data.rs aggregations
+ * (data.rs:520-602 call dijkstra_tree_shortest once per data point, centrality.rs:1141-1200) for many sources in ONE
+ * launch, one warp per source, every search replayed in the reference's heap order (visit order and predecessors exact
+ * under ties).  Outputs are [n_sources][capacity]: for source slot s and k < counts[s], visited_order[s][k] is the k-th
+ * settled node, pred[s][k] its predecessor (-1 = none, the source) and agg_seconds[s][k] its travel time.  Fails when a
+ * source settles more than `capacity` nodes. */
+int cs_dijkstra_trees_shortest(cs_graph* g, uint64_t n_sources, const uint32_t* sources, uint32_t max_seconds,
+                               float speed_m_s, uint32_t capacity, uint32_t* counts, uint32_t* visited_order,
+                               int64_t* pred, float* agg_seconds);
+
 /* Replaces NetworkStructure.dijkstra_tree_segment (centrality.rs:1523-1611): the single-predecessor tree of one capped
  * search over incoming edges with the visited-edge list.  `visited_nodes[0 .. *n_visited)` in pop order;
  * `visited_edges[0 .. *n_visited_edges)` are container edge ids (petgraph EdgeIndex) in the order the reference pushes
