@@ -555,11 +555,7 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
         off = align_up(off + bytes, 256);
         return o;
     };
-    // chain kernels: dense map over the junctions; node-level kernels: open-addressing table sized by the reach capacity
-    // (at most half full; the slack covers the claims of one relaxation batch beyond the capacity check)
-    L.hsize = kind == 3 ? 0u : 2u * rcap + 2048u;
-    L.ds = take(kind == 3 ? nstates * sizeof(uint2) : 0);
-    L.ht = take((size_t)L.hsize * sizeof(uint4));
+    L.ds = take(nstates * sizeof(uint2));
     L.node_list = take((size_t)rcap * 4);
     L.qa = take((size_t)qcap * 8);
     L.qb = take((size_t)qcap * 8);
@@ -586,15 +582,10 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
         return cs_fail("not enough device memory for the search arena (%zu bytes per worker)", L.stride);
     g->arena_bytes = (size_t)workers * L.stride;
     CS_CUDA(cudaMalloc(&g->d_arena, g->arena_bytes));
-    // the maps start empty ({inf, none}); each search resets exactly what it touched
+    // dense maps start at {inf, none}; each search resets exactly what it touched
     {
-        if (kind == 3) {
-            dim3 grid((unsigned)std::min<size_t>((nstates + 255) / 256, 64), workers);
-            cs_k_init_ds<<<grid, 256, 0, g->stream>>>(g->d_arena, L.stride, L.ds, nstates);
-        } else {
-            dim3 grid((unsigned)std::min<size_t>(((size_t)L.hsize + 255) / 256, 64), workers);
-            cs_k_init_ht<<<grid, 256, 0, g->stream>>>(g->d_arena, L.stride, L.ht, L.hsize);
-        }
+        dim3 grid((unsigned)std::min<size_t>((nstates + 255) / 256, 64), workers);
+        cs_k_init_ds<<<grid, 256, 0, g->stream>>>(g->d_arena, L.stride, L.ds, nstates);
         CS_CUDA(cudaGetLastError());
         CS_CUDA(cudaStreamSynchronize(g->stream));
     }

@@ -44,9 +44,7 @@ static int ensure_replay_arena(cs_graph* g, int D) {
         off = align_up(off + bytes, 256);
         return o;
     };
-    L.hsize = 2u * rcap + 2048u;
-    L.ds = take(0);
-    L.ht = take((size_t)L.hsize * sizeof(uint4));
+    L.ds = take(nstates * sizeof(uint2));
     L.node_list = take((size_t)rcap * 4);
     L.qa = take((size_t)qcap * 8);
     L.qb = take((size_t)qcap * 8);
@@ -67,8 +65,8 @@ static int ensure_replay_arena(cs_graph* g, int D) {
     if ((size_t)workers * L.stride > (size_t)((double)free_b * 0.5))
         return cs_fail("not enough device memory for the replay arena (%zu bytes per worker)", L.stride);
     CS_CUDA(cudaMalloc(&g->d_arena2, (size_t)workers * L.stride));
-    dim3 grid((unsigned)std::min<size_t>(((size_t)L.hsize + 255) / 256, 64), workers);
-    cs_k_init_ht<<<grid, 256, 0, g->stream>>>(g->d_arena2, L.stride, L.ht, L.hsize);
+    dim3 grid((unsigned)std::min<size_t>((nstates + 255) / 256, 64), workers);
+    cs_k_init_ds<<<grid, 256, 0, g->stream>>>(g->d_arena2, L.stride, L.ds, nstates);
     CS_CUDA(cudaGetLastError());
     CS_CUDA(cudaStreamSynchronize(g->stream));
     g->lay2 = L;

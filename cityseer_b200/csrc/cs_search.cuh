@@ -6,15 +6,13 @@
 #include "cs_common.cuh"
 
 struct CsArenaLayout {
-    size_t ds, ht, node_list, qa, qb, far, s_node, s_agg, predmask, sigma, dep, bdone, frank, needm, jrank, stride;
-    uint32_t rcap, qcap, hsize;
+    size_t ds, node_list, qa, qb, far, s_node, s_agg, predmask, sigma, dep, bdone, frank, needm, jrank, stride;
+    uint32_t rcap, qcap;
 };
 
 struct CsWarpArena {
-    uint2* ds;             // chain kernels: dense [J + 1] {seconds bits, settle rank}; {inf, none} outside a search
-    uint4* ht;             // node-level kernels: open-addressing table [hsize] {node, seconds bits, settle rank, -}
-    uint32_t hsize;
-    uint32_t* node_list;   // [rcap] table slots of the reached nodes in discovery order (after P2: by settle rank)
+    uint2* ds;             // dense [n]: {seconds bits, settle rank}; {inf, none} outside a search
+    uint32_t* node_list;   // [rcap] reached nodes in discovery order
     uint2* qa;             // [qcap] frontier queues: {node | (skip_pos+1) << 26, seconds bits}
     uint2* qb;
     uint2* far;
@@ -35,8 +33,6 @@ __device__ __forceinline__ CsWarpArena cs_arena(uint8_t* arena, const CsArenaLay
     uint8_t* base = arena + (size_t)worker * L.stride;
     CsWarpArena A;
     A.ds = reinterpret_cast<uint2*>(base + L.ds);
-    A.ht = reinterpret_cast<uint4*>(base + L.ht);
-    A.hsize = L.hsize;
     A.node_list = reinterpret_cast<uint32_t*>(base + L.node_list);
     A.qa = reinterpret_cast<uint2*>(base + L.qa);
     A.qb = reinterpret_cast<uint2*>(base + L.qb);
@@ -51,46 +47,6 @@ __device__ __forceinline__ CsWarpArena cs_arena(uint8_t* arena, const CsArenaLay
     A.rcap = L.rcap;
     A.qcap = L.qcap;
     return A;
-}
-
-// ---- per-source map node -> {seconds bits, settle rank} of the node-level kernels.  A dense array over all nodes costs
-// 8 bytes x node_bound per resident warp (8 MB on the 1M-node graph, 32 MB on the 4M-node one - the arena then decides how
-// many warps fit); the map is an open-addressing table sized by the reach capacity instead: 16-byte entries {node, seconds
-// bits, rank, -}, linear probing from a multiplicative hash, at most half full.  A search clears exactly the slots it
-// claimed (node_list holds them), so the table is empty between sources and needs no tombstones.
-#define CS_HT_EMPTY 0xffffffffu
-__device__ __forceinline__ uint32_t cs_ht_home(const CsWarpArena& A, uint32_t node) {
-    return __umulhi(node * 2654435761u, A.hsize);
-}
-// {seconds bits, rank} of `node`; {inf, none} when the search has not reached it
-__device__ __forceinline__ uint2 cs_ds_get(const CsWarpArena& A, uint32_t node) {
-    uint32_t h = cs_ht_home(A, node);
-    for (;;) {
-        const uint4 e = cs_ld(&A.ht[h]);
-        if (e.x == node) return make_uint2(e.y, e.z);
-        if (e.x == CS_HT_EMPTY) return make_uint2(CS_INF_BITS, CS_NOSLOT);
-        if (++h == A.hsize) h = 0;
-    }
-}
-// slot of `node`, claiming an empty one on first sight (lanes may claim concurrently; the table never fills up: the
-// reach-capacity check stops a search long before)
-__device__ __forceinline__ uint32_t cs_ds_claim(const CsWarpArena& A, uint32_t node) {
-    uint32_t h = cs_ht_home(A, node);
-    for (;;) {
-        const uint32_t k = cs_ld(&A.ht[h].x);
-        if (k == node) return h;
-        if (k == CS_HT_EMPTY) {
-            const uint32_t old = atomicCAS(&A.ht[h].x, CS_HT_EMPTY, node);
-            if (old == CS_HT_EMPTY || old == node) return h;
-        }
-        if (++h == A.hsize) h = 0;
-    }
-}
-__global__ void cs_k_init_ht(uint8_t* arena, size_t stride, size_t ht_off, size_t hsize) {
-    uint4* ht = reinterpret_cast<uint4*>(arena + (size_t)blockIdx.y * stride + ht_off);
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t step = (size_t)gridDim.x * blockDim.x;
-    for (; i < hsize; i += step) ht[i] = make_uint4(CS_HT_EMPTY, CS_INF_BITS, CS_NOSLOT, 0u);
 }
 
 // dense maps of all workers in one launch: blockIdx.y = worker
@@ -116,9 +72,8 @@ __device__ __forceinline__ uint32_t cs_p1_search(const CsGraphDev& g, const CsWa
     float thr = delta;
     fail = 0;
     if (lane == 0) {
-        const uint32_t slot = cs_ds_claim(A, src);
-        cs_st(&A.ht[slot].y, 0u);
-        cs_st(&A.node_list[0], slot);
+        cs_st(&A.ds[src], make_uint2(0u, CS_NOSLOT));
+        cs_st(&A.node_list[0], src);
         cs_st(&qc[0], make_uint2(src, 0u));
     }
     __syncwarp();
@@ -133,7 +88,7 @@ __device__ __forceinline__ uint32_t cs_p1_search(const CsGraphDev& g, const CsWa
                     v = it.x & CS_NODE_MASK;
                     skip = (it.x >> CS_NODE_BITS) - 1u;
                     abits = it.y;
-                    valid = cs_ds_get(A, v).x == abits;  // stale entries were superseded by a smaller distance
+                    valid = cs_ld(&A.ds[v].x) == abits;  // stale entries were superseded by a smaller distance
                 }
                 uint32_t eb = 0, deg = 0;
                 if (valid) {
@@ -144,7 +99,7 @@ __device__ __forceinline__ uint32_t cs_p1_search(const CsGraphDev& g, const CsWa
                 const float a = __uint_as_float(abits);
                 for (uint32_t j = 0; j < maxdeg; ++j) {
                     bool improved = false, first = false;
-                    uint32_t nb = 0, cbits = 0, back = 0, nslot = 0;
+                    uint32_t nb = 0, cbits = 0, back = 0;
                     float cand = 0.f;
                     if (j < deg && j != skip) {
                         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&g.in_rec[eb + j]));
@@ -152,8 +107,7 @@ __device__ __forceinline__ uint32_t cs_p1_search(const CsGraphDev& g, const CsWa
                         cand = __fadd_rn(a, __uint_as_float(raw.y));
                         if (nb != v && !(cand > max_seconds)) {
                             cbits = __float_as_uint(cand);
-                            nslot = cs_ds_claim(A, nb);
-                            const uint32_t old = atomicMin(&A.ht[nslot].y, cbits);
+                            const uint32_t old = atomicMin(&A.ds[nb].x, cbits);
                             improved = cbits < old;
                             first = old == CS_INF_BITS;
                             back = (raw.w >> 16) & 0x3fu;  // (position of the twin edge in nb's in-list) + 1, or 0
@@ -162,7 +116,7 @@ __device__ __forceinline__ uint32_t cs_p1_search(const CsGraphDev& g, const CsWa
                     uint32_t m = __ballot_sync(CS_FULL, first);
                     if (m) {
                         const uint32_t pos = count + __popc(m & ltmask);
-                        if (first && pos < A.rcap) cs_st(&A.node_list[pos], nslot);
+                        if (first && pos < A.rcap) cs_st(&A.node_list[pos], nb);
                         count += __popc(m);
                     }
                     const bool pn = improved && (cand < thr);
@@ -199,7 +153,7 @@ __device__ __forceinline__ uint32_t cs_p1_search(const CsGraphDev& g, const CsWa
         float mn = __uint_as_float(CS_INF_BITS);
         for (uint32_t i = lane; i < nf; i += 32) {
             const uint2 it = cs_ld(&far[i]);
-            if (cs_ds_get(A, it.x & CS_NODE_MASK).x == it.y) mn = fminf(mn, __uint_as_float(it.y));
+            if (cs_ld(&A.ds[it.x & CS_NODE_MASK].x) == it.y) mn = fminf(mn, __uint_as_float(it.y));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(CS_FULL, mn, o));
@@ -213,7 +167,7 @@ __device__ __forceinline__ uint32_t cs_p1_search(const CsGraphDev& g, const CsWa
             uint2 it = make_uint2(0u, 0u);
             if (livee) {
                 it = cs_ld(&far[idx]);
-                livee = cs_ds_get(A, it.x & CS_NODE_MASK).x == it.y;
+                livee = cs_ld(&A.ds[it.x & CS_NODE_MASK].x) == it.y;
             }
             const bool near = livee && (__uint_as_float(it.y) < thr);
             const bool keep = livee && !near;
@@ -244,12 +198,11 @@ __device__ __forceinline__ void cs_p2_order(const CsGraphDev& g, const CsWarpAre
     const uint32_t lane = cs_lane();
     for (uint32_t i = lane; i < CS_NBINS; i += 32) bins[i] = 0;
     __syncwarp();
-    uint32_t* tmp_slot = reinterpret_cast<uint32_t*>(A.qb);  // table slot of each key, bin-scattered beside tmp_key
     for (uint32_t i = lane; i < R; i += 32) {
-        const uint4 e = cs_ld(&A.ht[cs_ld(&A.node_list[i])]);
-        cs_st(&A.s_node[i], e.x);                                // discovery-indexed temps, rewritten by rank below
-        cs_st(reinterpret_cast<uint32_t*>(&A.s_agg[i]), e.y);
-        atomicAdd(&bins[cs_bin(e.y, bin_scale)], 1u);
+        const uint32_t node = cs_ld(&A.node_list[i]);
+        const uint32_t ab = cs_ld(&A.ds[node].x);
+        cs_st(reinterpret_cast<uint32_t*>(&A.s_agg[i]), ab);  // discovery-indexed temp, rewritten by rank below
+        atomicAdd(&bins[cs_bin(ab, bin_scale)], 1u);
     }
     __syncwarp();
     {
@@ -268,12 +221,11 @@ __device__ __forceinline__ void cs_p2_order(const CsGraphDev& g, const CsWarpAre
     }
     __syncwarp();
     for (uint32_t i = lane; i < R; i += 32) {
-        const uint32_t node = cs_ld(&A.s_node[i]);
+        const uint32_t node = cs_ld(&A.node_list[i]);
         const uint32_t ab = cs_ld(reinterpret_cast<const uint32_t*>(&A.s_agg[i]));
         const uint32_t pos = atomicAdd(&bins[cs_bin(ab, bin_scale)], 1u);
         // the source sorts first among zero-distance nodes (it is always the first settled state)
         cs_st(&A.tmp_key[pos], ((unsigned long long)ab << 32) | (node == src ? 0u : node + 1u));
-        cs_st(&tmp_slot[pos], cs_ld(&A.node_list[i]));
     }
     __syncwarp();
     // bins[b] now holds the end offset of bin b
@@ -287,11 +239,9 @@ __device__ __forceinline__ void cs_p2_order(const CsGraphDev& g, const CsWarpAre
         for (uint32_t j = start; j < end; ++j) rank += (cs_ld(&A.tmp_key[j]) < key) ? 1u : 0u;
         const uint32_t low = (uint32_t)key;
         const uint32_t node = low ? low - 1u : src;
-        const uint32_t slot = cs_ld(&tmp_slot[pos]);
         cs_st(&A.s_node[rank], node);
         cs_st(&A.s_agg[rank], __uint_as_float(ab));
-        cs_st(&A.ht[slot].z, rank);
-        cs_st(&A.node_list[rank], slot);  // by settle rank from here on: the reset walks it
+        cs_st(&A.ds[node].y, rank);
         cs_st(&A.sigma[rank], 0.0);
         cs_st(reinterpret_cast<unsigned long long*>(A.bdone) + rank, 0ull);
         edge_iters += __ldg(&g.in_off[node + 1]) - __ldg(&g.in_off[node]);
@@ -299,14 +249,7 @@ __device__ __forceinline__ void cs_p2_order(const CsGraphDev& g, const CsWarpAre
     __syncwarp();
 }
 
-// chain kernels: clear the touched entries of the dense junction map
 __device__ __forceinline__ void cs_p6_reset(const CsWarpArena& A, uint32_t R) {
     for (uint32_t r = cs_lane(); r < R; r += 32) cs_st(&A.ds[cs_ld(&A.s_node[r])], make_uint2(CS_INF_BITS, CS_NOSLOT));
-    __syncwarp();
-}
-// node-level kernels: clear the claimed table slots (node_list holds them by settle rank after cs_p2_order)
-__device__ __forceinline__ void cs_p6_reset_ht(const CsWarpArena& A, uint32_t R) {
-    for (uint32_t r = cs_lane(); r < R; r += 32)
-        cs_st(&A.ht[cs_ld(&A.node_list[r])], make_uint4(CS_HT_EMPTY, CS_INF_BITS, CS_NOSLOT, 0u));
     __syncwarp();
 }

@@ -86,7 +86,7 @@ __device__ __forceinline__ void cs_seg_replay(const CsGraphDev& g, const CsWarpA
                 const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&g.in_rec[e]));
                 const uint32_t nb = raw.x;
                 if (nb == cur) continue;
-                const uint2 dnb = cs_ds_get(A, nb);
+                const uint2 dnb = cs_ld(&A.ds[nb]);
                 if (dnb.x == CS_INF_BITS) continue;  // every candidate of nb exceeds the cutoff
                 if (cs_ld(&popseq[dnb.y]) != CS_NOSLOT) continue;
                 const float ts = __fadd_rn(base, __uint_as_float(raw.y));
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
             cs_seg_replay(p.g, A, bins, R, p.max_seconds, popseq, reinterpret_cast<float*>(A.dep) + A.rcap, rfail);
             if (rfail) {
                 if (lane == 0) atomicCAS(p.error, 0, rfail);
-                cs_p6_reset_ht(A, R);
+                cs_p6_reset(A, R);
                 run = false;
                 R = 0;
             }
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
                         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&p.g.out_rec[eb + j]));
                         const uint32_t u = raw.x;
                         if (u == v) continue;
-                        const uint2 du = cs_ds_get(A, u);
+                        const uint2 du = cs_ld(&A.ds[u]);
                         if (du.x == CS_INF_BITS || du.y >= r) continue;
                         const float c = __fadd_rn(__uint_as_float(du.x), __uint_as_float(raw.y));
                         if (__float_as_uint(c) != av_bits) continue;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
                         const uint32_t m = raw.x;
                         float dm = dn;
                         if (m != v) {
-                            const uint2 dmm = cs_ds_get(A, m);
+                            const uint2 dmm = cs_ld(&A.ds[m]);
                             if (dmm.x != CS_INF_BITS && dmm.y < r) continue;  // m settled first: it visited this edge pair
                             dm = dmm.x == CS_INF_BITS ? f_inf : __fmul_rn(__uint_as_float(dmm.x), p.speed);
                         }
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
         if (run && !p.replay && __any_sync(CS_FULL, ambiguous)) {
             // leave this source to the replay launch: nothing of it has been accumulated yet
             if (lane == 0) cs_st(&p.redo_list[atomicAdd(&p.counters[CS_C_FALLBACK], 1ull)], src);
-            cs_p6_reset_ht(A, R);
+            cs_p6_reset(A, R);
             run = false;
             R = 0;
         }
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
                         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&p.g.in_rec[eb + j]));
                         const uint32_t x = raw.x;
                         if (x == w) continue;
-                        const uint2 dx = cs_ds_get(A, x);
+                        const uint2 dx = cs_ld(&A.ds[x]);
                         if (dx.x == CS_INF_BITS || dx.y <= r) continue;
                         if ((cs_ld(&A.predmask[dx.y]) >> (raw.w & 0xffu)) & 1u) {
                             if (dx.y < (uint32_t)b0 + 32u) same_chunk |= 1u << nchild;
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
 
         __syncthreads();
         if (!run) continue;
-        cs_p6_reset_ht(A, R);
+        cs_p6_reset(A, R);
         edge_iters = cs_warp_sum(edge_iters);
         relax = cs_warp_sum(relax);
         n_ci = cs_warp_sum(n_ci);

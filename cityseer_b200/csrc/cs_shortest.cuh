@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
                     const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&p.g.out_rec[eb + j]));
                     const uint32_t u = raw.x;
                     if (u == v) continue;
-                    const uint2 du = cs_ds_get(A, u);
+                    const uint2 du = cs_ld(&A.ds[u]);
                     if (du.x == CS_INF_BITS) continue;
                     const float au = __uint_as_float(du.x);
                     if (p.closeness && (raw.w & 0x100u)) {
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
             for (uint32_t r = lane; r < R; r += 32) cs_st(&odw[r], 0.0);
             __syncwarp();
             for (unsigned long long j = __ldg(&p.od_off[si]) + lane; j < __ldg(&p.od_off[si + 1]); j += 32) {
-                const uint2 dd = cs_ds_get(A, __ldg(&p.od_dst[j]));
+                const uint2 dd = cs_ld(&A.ds[__ldg(&p.od_dst[j])]);
                 if (dd.x != CS_INF_BITS) cs_st(&odw[dd.y], (double)__ldg(&p.od_w[j]));  // destinations are unique per origin
             }
             __syncwarp();
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
                         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&p.g.in_rec[eb + j]));
                         const uint32_t x = raw.x;
                         if (x == w) continue;
-                        const uint2 dx = cs_ds_get(A, x);
+                        const uint2 dx = cs_ld(&A.ds[x]);
                         if (dx.x == CS_INF_BITS || dx.y <= r) continue;
                         if ((cs_ld(&A.predmask[dx.y]) >> (raw.w & 0xffu)) & 1u) {
                             if (dx.y < (uint32_t)b0 + 32u) same_chunk |= 1u << nsucc;
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
 
         // ------------------------------------------------------------------ P6: reset the dense map
         tc[5] = clock64();
-        cs_p6_reset_ht(A, R);
+        cs_p6_reset(A, R);
         tc[6] = clock64();
 
         edge_iters = cs_warp_sum(edge_iters);
