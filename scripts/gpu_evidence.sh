@@ -1,8 +1,17 @@
 #!/bin/bash
 # End-of-round evidence on one B200: parity suite, the three bench lines (+ reference arms), ncu launch lists and full
-# captures of the dominant kernel of each function, compute-sanitizer over the new kernels.  usage: gpu_evidence.sh <tag>
-tag=${1:-r02z}
+# captures of the dominant kernel of each function, compute-sanitizer over the new kernels.
+# usage: gpu_evidence.sh <tag> [a|b]   (gpurun brings back at most 64 MiB per call: part b = the two large ncu reports)
+tag=${1:-r02z}; part=${2:-a}
 mkdir -p gpurun_out
+if [ "$part" = b ]; then
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:cs_k_shortest3 -s 1 -c 1 -o gpurun_out/${tag}_shortest3 \
+      python bench.py --function shortest --steps 1 --warmup 1 --no-cpu > gpurun_out/${tag}_ncu_shortest3.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:cs_k_segment3 -s 1 -c 1 -o gpurun_out/${tag}_segment3 \
+      python bench.py --function segment --steps 1 --warmup 1 --no-cpu > gpurun_out/${tag}_ncu_segment3.log 2>&1
+  ls -la gpurun_out/${tag}_*.ncu-rep
+  exit 0
+fi
 bash scripts/gpu_tests.sh $tag > /dev/null
 grep -cE "PASSED" gpurun_out/${tag}_tests.log; grep -E "FAILED|ERROR|Timeout|^E " gpurun_out/${tag}_tests.log | head -30
 for fn in shortest segment simplest; do
@@ -13,10 +22,6 @@ for fn in shortest segment simplest; do
   timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${tag}_launches_$fn.csv \
     python bench.py --function $fn --steps 2 --warmup 1 --no-cpu > /dev/null 2>&1
 done
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:cs_k_shortest3 -s 1 -c 1 -o gpurun_out/${tag}_shortest3 \
-    python bench.py --function shortest --steps 1 --warmup 1 --no-cpu > gpurun_out/${tag}_ncu_shortest3.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:cs_k_segment3 -s 1 -c 1 -o gpurun_out/${tag}_segment3 \
-    python bench.py --function segment --steps 1 --warmup 1 --no-cpu > gpurun_out/${tag}_ncu_segment3.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:cs_k_simplest -s 1 -c 1 -o gpurun_out/${tag}_simplest \
     python bench.py --function simplest --steps 1 --warmup 1 --no-cpu > gpurun_out/${tag}_ncu_simplest.log 2>&1
 for tool in memcheck synccheck; do
