@@ -156,9 +156,9 @@ def host_threads() -> int:
 
 def cpu_sample_size(fn: str, threads: int, secs: float) -> int:
     """Sources for roughly ``secs`` seconds of CPU work: the faithful port pays Theta(N) (shortest, simplest) or
-    Theta(N + E) (segment) allocations per source, roughly 15 / 3 / 60 sources per second and thread on the three
-    workloads (1M-node graph for shortest and segment, 100k-node dual for simplest)."""
-    per_thread = {"shortest": 15.0, "segment": 3.0, "simplest": 60.0}[fn]
+    Theta(N + E) (segment) allocations per source, roughly 15 / 12 / 130 sources per second and thread on the three
+    workloads (1M-node graph for shortest and segment, 100k-node dual for simplest; measured on the GPU box's host)."""
+    per_thread = {"shortest": 15.0, "segment": 12.0, "simplest": 120.0}[fn]
     return max(threads, int(per_thread * threads * secs))
 
 
