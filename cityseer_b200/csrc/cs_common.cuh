@@ -57,15 +57,7 @@ template <class T>
 __device__ __forceinline__ void cs_st(T* p, T v) { __stcg(p, v); }
 
 __device__ __forceinline__ void cs_red_add(double* p, double v) {
-#ifdef CS_EXPERIMENT_NO_RED  // measurement only: how much of the time the f64 scatter costs
-    if (v == -1.2345) *p = v;
-#else
-#ifdef CS_RED_NOCLOBBER  // experiment: let the compiler move independent work across the reduction
-    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v));
-#else
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-#endif
-#endif
 }
 // f32 exp as the reference's platform libm computes it.  Rust's f32::exp calls expf; on Linux that is glibc's table-driven
 // algorithm (sysdeps/ieee754/flt-32/e_expf.c, from ARM optimized-routines): exp(x) = 2^(k/32) * 2^(r/32) with a 32-entry

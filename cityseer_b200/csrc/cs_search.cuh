@@ -97,44 +97,65 @@ __device__ __forceinline__ uint32_t cs_p1_search(const CsGraphDev& g, const CsWa
                 }
                 const uint32_t maxdeg = __reduce_max_sync(CS_FULL, deg);
                 const float a = __uint_as_float(abits);
-                for (uint32_t j = 0; j < maxdeg; ++j) {
-                    bool improved = false, first = false;
-                    uint32_t nb = 0, cbits = 0, back = 0;
-                    float cand = 0.f;
-                    if (j < deg && j != skip) {
-                        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&g.in_rec[eb + j]));
-                        nb = raw.x;
-                        cand = __fadd_rn(a, __uint_as_float(raw.y));
-                        if (nb != v && !(cand > max_seconds)) {
-                            cbits = __float_as_uint(cand);
-                            const uint32_t old = atomicMin(&A.ds[nb].x, cbits);
-                            improved = cbits < old;
-                            first = old == CS_INF_BITS;
-                            back = (raw.w >> 16) & 0x3fu;  // (position of the twin edge in nb's in-list) + 1, or 0
+                // four edges per lane at a time: the edge records, then the atomicMin on the neighbours' distances, are
+                // issued for the whole group before their results are consumed (two round trips per group, not per edge)
+                for (uint32_t j0 = 0; j0 < maxdeg; j0 += 4) {
+                    uint4 raws[4];
+                    bool use[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        use[t] = j0 + t < deg && j0 + t != skip;
+                        if (use[t]) raws[t] = __ldg(reinterpret_cast<const uint4*>(&g.in_rec[eb + j0 + t]));
+                    }
+                    uint32_t olds[4], cbs[4];
+                    float cands[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        cands[t] = 0.f;
+                        cbs[t] = 0;
+                        olds[t] = 0;
+                        if (use[t]) {
+                            cands[t] = __fadd_rn(a, __uint_as_float(raws[t].y));
+                            use[t] = raws[t].x != v && !(cands[t] > max_seconds);
+                            if (use[t]) {
+                                cbs[t] = __float_as_uint(cands[t]);
+                                olds[t] = atomicMin(&A.ds[raws[t].x].x, cbs[t]);
+                            }
                         }
                     }
-                    uint32_t m = __ballot_sync(CS_FULL, first);
-                    if (m) {
-                        const uint32_t pos = count + __popc(m & ltmask);
-                        if (first && pos < A.rcap) cs_st(&A.node_list[pos], nb);
-                        count += __popc(m);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        if (j0 + t >= maxdeg) break;  // warp-uniform
+                        const uint32_t nb = use[t] ? raws[t].x : 0u;
+                        const uint32_t cbits = cbs[t];
+                        const float cand = cands[t];
+                        const bool improved = use[t] && cbits < olds[t];
+                        const bool first = use[t] && olds[t] == CS_INF_BITS;
+                        // (position of the twin edge in nb's in-list) + 1, or 0
+                        const uint32_t back = use[t] ? (raws[t].w >> 16) & 0x3fu : 0u;
+                        uint32_t m = __ballot_sync(CS_FULL, first);
+                        if (m) {
+                            const uint32_t pos = count + __popc(m & ltmask);
+                            if (first && pos < A.rcap) cs_st(&A.node_list[pos], nb);
+                            count += __popc(m);
+                        }
+                        const bool pn = improved && (cand < thr);
+                        const bool pf = improved && !pn;
+                        const uint2 item = make_uint2(nb | (back << CS_NODE_BITS), cbits);
+                        m = __ballot_sync(CS_FULL, pn);
+                        if (m) {
+                            const uint32_t pos = nn + __popc(m & ltmask);
+                            if (pn && pos < A.qcap) cs_st(&qn[pos], item);
+                            nn += __popc(m);
+                        }
+                        m = __ballot_sync(CS_FULL, pf);
+                        if (m) {
+                            const uint32_t pos = nf + __popc(m & ltmask);
+                            if (pf && pos < A.qcap) cs_st(&far[pos], item);
+                            nf += __popc(m);
+                        }
+                        relax += improved ? 1ull : 0ull;
                     }
-                    const bool pn = improved && (cand < thr);
-                    const bool pf = improved && !pn;
-                    const uint2 item = make_uint2(nb | (back << CS_NODE_BITS), cbits);
-                    m = __ballot_sync(CS_FULL, pn);
-                    if (m) {
-                        const uint32_t pos = nn + __popc(m & ltmask);
-                        if (pn && pos < A.qcap) cs_st(&qn[pos], item);
-                        nn += __popc(m);
-                    }
-                    m = __ballot_sync(CS_FULL, pf);
-                    if (m) {
-                        const uint32_t pos = nf + __popc(m & ltmask);
-                        if (pf && pos < A.qcap) cs_st(&far[pos], item);
-                        nf += __popc(m);
-                    }
-                    relax += improved ? 1ull : 0ull;
                 }
             }
             if (count > A.rcap || nn > A.qcap || nf > A.qcap) {
@@ -196,6 +217,9 @@ __device__ __forceinline__ uint32_t cs_bin(uint32_t ab, float bin_scale) {
 __device__ __forceinline__ void cs_p2_order(const CsGraphDev& g, const CsWarpArena& A, uint32_t* bins, uint32_t src,
                                             uint32_t R, float bin_scale, unsigned long long& edge_iters) {
     const uint32_t lane = cs_lane();
+    // node_list is dead once its entries have been scattered into the sort keys: the shortest kernel reuses it as the
+    // per-rank "smallest successor" array of its dependency pass, initialised here while the ranks are being written
+    uint32_t* minsucc_out = A.node_list;
     for (uint32_t i = lane; i < CS_NBINS; i += 32) bins[i] = 0;
     __syncwarp();
     for (uint32_t i = lane; i < R; i += 32) {
@@ -244,6 +268,7 @@ __device__ __forceinline__ void cs_p2_order(const CsGraphDev& g, const CsWarpAre
         cs_st(&A.ds[node].y, rank);
         cs_st(&A.sigma[rank], 0.0);
         cs_st(reinterpret_cast<unsigned long long*>(A.bdone) + rank, 0ull);
+        cs_st(&minsucc_out[rank], CS_NOSLOT);
         edge_iters += __ldg(&g.in_off[node + 1]) - __ldg(&g.in_off[node]);
     }
     __syncwarp();

@@ -62,9 +62,12 @@ struct CsSegmentParams {
 __device__ __forceinline__ void cs_seg_replay(const CsGraphDev& g, const CsWarpArena& A, uint32_t* smem_words, uint32_t R,
                                               float max_seconds, uint32_t* popseq, float* run_agg, int& fail) {
     const uint32_t lane = cs_lane();
+    // popseq / run_agg are written and read with ordinary (L1-cached) accesses here: one lane walks them serially, so a
+    // hit in L1 instead of an L2 round trip per access halves the replay; the stores write through, and the later phases
+    // read them from L2 as usual.  Every entry in use is re-initialised first, so no stale line of an earlier source is read.
     for (uint32_t r = lane; r < R; r += 32) {
-        cs_st(&popseq[r], CS_NOSLOT);
-        cs_st(&run_agg[r], __uint_as_float(CS_INF_BITS));
+        popseq[r] = CS_NOSLOT;
+        run_agg[r] = __uint_as_float(CS_INF_BITS);
     }
     __syncwarp();
     if (lane == 0) {
@@ -72,14 +75,14 @@ __device__ __forceinline__ void cs_seg_replay(const CsGraphDev& g, const CsWarpA
         cs_heap_init(h, smem_words, CS_SEG_HEAP_SMEM, A.qa);  // qa, qb and far are contiguous and dead after the order pass
         const uint32_t cap = 3u * A.qcap;
         uint32_t seq = 0;
-        cs_st(&run_agg[0], 0.0f);
+        run_agg[0] = 0.0f;
         cs_heap_push(h, 0u, 0u);
         while (h.len > 0) {
             const uint32_t r = cs_heap_pop(h).x;
-            if (cs_ld(&popseq[r]) != CS_NOSLOT) continue;  // lazy deletion (:1545)
-            cs_st(&popseq[r], seq++);
+            if (popseq[r] != CS_NOSLOT) continue;  // lazy deletion (:1545)
+            popseq[r] = seq++;
             const uint32_t cur = cs_ld(&A.s_node[r]);
-            const float base = cs_ld(&run_agg[r]);
+            const float base = run_agg[r];
             const uint32_t eb = __ldg(&g.in_off[cur]);
             const uint32_t e1 = __ldg(&g.in_off[cur + 1]);
             for (uint32_t e = eb; e < e1; ++e) {
@@ -88,11 +91,11 @@ __device__ __forceinline__ void cs_seg_replay(const CsGraphDev& g, const CsWarpA
                 if (nb == cur) continue;
                 const uint2 dnb = cs_ld(&A.ds[nb]);
                 if (dnb.x == CS_INF_BITS) continue;  // every candidate of nb exceeds the cutoff
-                if (cs_ld(&popseq[dnb.y]) != CS_NOSLOT) continue;
+                if (popseq[dnb.y] != CS_NOSLOT) continue;
                 const float ts = __fadd_rn(base, __uint_as_float(raw.y));
                 if (ts > max_seconds) continue;
-                if (ts < cs_ld(&run_agg[dnb.y])) {
-                    cs_st(&run_agg[dnb.y], ts);
+                if (ts < run_agg[dnb.y]) {
+                    run_agg[dnb.y] = ts;
                     if (h.len >= cap) {
                         fail = CS_ERR_QUEUE_OVERFLOW;
                         break;
@@ -102,6 +105,7 @@ __device__ __forceinline__ void cs_seg_replay(const CsGraphDev& g, const CsWarpA
             }
             if (fail) break;
         }
+        __threadfence_block();
     }
     fail = __shfl_sync(CS_FULL, fail, 0);
     __syncwarp();

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
     uint32_t* histE = s_hist_all[wic][1];
     float* rankf = s_rank_all[wic];
     const CsWarpArena A = cs_arena(p.arena, p.lay, worker);
+    uint32_t* minsucc = A.node_list;  // [rcap] after P2 (which leaves it at "none"): smallest successor rank per node
     const int D = p.D;
     const int D2 = 2 * D;
     const float one_minus = 1.0f - CS_TIE_EPS, one_plus = 1.0f + CS_TIE_EPS;
@@ -118,35 +119,48 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
                 if (p.closeness) atomicAdd(&histN[cs_first_threshold<DT>(p, cost_v)], 1u);
                 const uint32_t eb = __ldg(&p.g.out_off[v]);
                 const uint32_t deg = __ldg(&p.g.out_off[v + 1]) - eb;
-                for (uint32_t j = 0; j < deg; ++j) {
-                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&p.g.out_rec[eb + j]));
-                    const uint32_t u = raw.x;
-                    if (u == v) continue;
-                    const uint2 du = cs_ld(&A.ds[u]);
-                    if (du.x == CS_INF_BITS) continue;
-                    const float au = __uint_as_float(du.x);
-                    if (p.closeness && (raw.w & 0x100u)) {
-                        const float ec = fmaxf(cost_v, __fmul_rn(au, p.speed));
-                        atomicAdd(&histE[cs_first_threshold<DT>(p, ec)], 1u);
+                // four out-edges at a time: the edge records, then the neighbours' map entries, are in flight together
+                for (uint32_t j0 = 0; j0 < deg; j0 += 4) {
+                    uint4 raws[4];
+                    uint2 dus[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        raws[t] = j0 + t < deg ? __ldg(reinterpret_cast<const uint4*>(&p.g.out_rec[eb + j0 + t])) : make_uint4(v, 0u, 0u, 0u);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        dus[t] = raws[t].x != v ? cs_ld(&A.ds[raws[t].x]) : make_uint2(CS_INF_BITS, CS_NOSLOT);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint4 raw = raws[t];
+                        const uint32_t j = j0 + t;
+                        const uint32_t u = raw.x;
+                        if (u == v) continue;  // self-loops and the padding of the last group
+                        const uint2 du = dus[t];
+                        if (du.x == CS_INF_BITS) continue;
+                        const float au = __uint_as_float(du.x);
+                        if (p.closeness && (raw.w & 0x100u)) {
+                            const float ec = fmaxf(cost_v, __fmul_rn(au, p.speed));
+                            atomicAdd(&histE[cs_first_threshold<DT>(p, ec)], 1u);
+                        }
+                        if (du.y >= r || v == src) continue;  // u must be settled before v; the source has no predecessors
+                        const float c = __fadd_rn(au, __uint_as_float(raw.y));
+                        if (!p.phase2 && c > p.max_seconds) continue;
+                        // insertion by (settle rank of u, position in u's incoming list)
+                        const uint32_t skey = du.y;
+                        const uint32_t ipos = raw.w & 0xffu;
+                        int k = ncand++;
+                        while (k > 0 && (crk[k - 1] > skey || (crk[k - 1] == skey && (cj[k - 1] >> 8) > ipos))) {
+                            cc[k] = cc[k - 1];
+                            cu[k] = cu[k - 1];
+                            crk[k] = crk[k - 1];
+                            cj[k] = cj[k - 1];
+                            --k;
+                        }
+                        cc[k] = c;
+                        cu[k] = u;
+                        crk[k] = skey;
+                        cj[k] = j | (ipos << 8);
                     }
-                    if (du.y >= r || v == src) continue;  // u must be settled before v; the source has no predecessors
-                    const float c = __fadd_rn(au, __uint_as_float(raw.y));
-                    if (!p.phase2 && c > p.max_seconds) continue;
-                    // insertion by (settle rank of u, position in u's incoming list)
-                    const uint32_t skey = du.y;
-                    const uint32_t ipos = raw.w & 0xffu;
-                    int k = ncand++;
-                    while (k > 0 && (crk[k - 1] > skey || (crk[k - 1] == skey && (cj[k - 1] >> 8) > ipos))) {
-                        cc[k] = cc[k - 1];
-                        cu[k] = cu[k - 1];
-                        crk[k] = crk[k - 1];
-                        cj[k] = cj[k - 1];
-                        --k;
-                    }
-                    cc[k] = c;
-                    cu[k] = u;
-                    crk[k] = skey;
-                    cj[k] = j | (ipos << 8);
                 }
                 if (ncand == 1 && !p.phase2) {
                     pmask_c = 1u;
@@ -183,6 +197,9 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
                 uint32_t amask = 0;
                 for (uint32_t mm = pmask_c; mm; mm &= mm - 1) amask |= 1u << (cj[__ffs(mm) - 1] & 0xffu);
                 cs_st(&A.predmask[r], amask);
+                // the dependency pass forms chunks whose nodes do not depend on each other: the smallest rank that has
+                // this node as a predecessor bounds the chunk that may contain it
+                for (uint32_t mm = pmask_c; mm; mm &= mm - 1) atomicMin(&minsucc[crk[__ffs(mm) - 1]], r);
                 if (v == src) cs_st(&A.sigma[r], 1.0);
                 if (p.dump_npred) p.dump_npred[v] = __popc(pmask_c);
             }
@@ -307,95 +324,111 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
         }
         if (p.betweenness) {
             const double wt_d = (double)wt;
-            for (int b0 = (int)((R - 1) & ~31u); b0 >= 0; b0 -= 32) {
-                const uint32_t r = (uint32_t)b0 + lane;
-                const bool valid = r < R;
+            // reverse settle order in chunks of up to 32 nodes none of which depends on another one of the same chunk
+            // (minsucc): every successor of a chunk's node was finished by an earlier chunk, nothing waits
+            int hi = (int)R - 1;
+            while (hi >= 0) {
+                const int rr = hi - (int)lane;
+                const uint32_t ms = rr >= 0 ? cs_ld(&minsucc[rr]) : 0u;
+                const uint32_t badm = __ballot_sync(CS_FULL, rr < 0 || ms <= (uint32_t)hi);
+                const uint32_t cnt = badm ? (uint32_t)__ffs(badm) - 1u : 32u;  // >= 1: minsucc[hi] > hi
+                const bool valid = lane < cnt;
+                const uint32_t r = (uint32_t)(hi - (int)lane);
                 uint32_t w = 0;
-                uint32_t srk[CS_MAX_DEGREE];
-                int nsucc = 0;
-                uint32_t same_chunk = 0;  // successors inside this chunk (the only ones that can still be pending)
-                double sigma_w = 1.0;
-                float cost_w = 0.f;
-                if (valid) {
-                    w = cs_ld(&A.s_node[r]);
-                    cost_w = __fmul_rn(cs_ld(&A.s_agg[r]), p.speed);
-                    sigma_w = cs_ld(&A.sigma[r]);
-                    const uint32_t eb = __ldg(&p.g.in_off[w]);
-                    const uint32_t deg = __ldg(&p.g.in_off[w + 1]) - eb;
-                    for (uint32_t j = 0; j < deg; ++j) {
-                        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&p.g.in_rec[eb + j]));
-                        const uint32_t x = raw.x;
-                        if (x == w) continue;
-                        const uint2 dx = cs_ld(&A.ds[x]);
-                        if (dx.x == CS_INF_BITS || dx.y <= r) continue;
-                        if ((cs_ld(&A.predmask[dx.y]) >> (raw.w & 0xffu)) & 1u) {
-                            if (dx.y < (uint32_t)b0 + 32u) same_chunk |= 1u << nsucc;
-                            srk[nsucc++] = dx.y;
-                        }
-                    }
-                }
-                bool pending = valid;
                 double cr[2 * DT];  // positive credits of this lane's node, slot 2 * i (plain) / 2 * i + 1 (beta-weighted)
 #pragma unroll
                 for (int q = 0; q < 2 * DT; ++q) cr[q] = 0.0;
-                for (;;) {
-                    if (pending) {
-                        bool ok = true;
-                        for (uint32_t mm = same_chunk; mm; mm &= mm - 1) ok = ok && (cs_ld(&A.bdone[srk[__ffs(mm) - 1]]) != 0);
-                        if (ok) {
-                            double acc[DT], accb[DT];
+                if (valid) {
+                    w = cs_ld(&A.s_node[r]);
+                    const float cost_w = __fmul_rn(cs_ld(&A.s_agg[r]), p.speed);
+                    const double sigma_w = cs_ld(&A.sigma[r]);
+                    double acc[DT], accb[DT];
 #pragma unroll
-                            for (int i = 0; i < DT; ++i) acc[i] = accb[i] = 0.0;
-                            for (int k = 0; k < nsucc; ++k) {
-                                const double sx = cs_ld(&A.sigma[srk[k]]);
-                                const double f = (sx == sigma_w) ? 1.0 : sigma_w / sx;
-                                const double* dx = A.dep + (size_t)srk[k] * D2;
+                    for (int i = 0; i < DT; ++i) acc[i] = accb[i] = 0.0;
+                    const uint32_t eb = __ldg(&p.g.in_off[w]);
+                    const uint32_t deg = __ldg(&p.g.in_off[w + 1]) - eb;
+                    // four in-edges at a time, each level of the dependent chain (edge record -> neighbour's map entry ->
+                    // its predecessor mask -> its sigma) issued for the whole group before anything is consumed: the
+                    // round trips overlap instead of adding up edge by edge
+                    for (uint32_t j0 = 0; j0 < deg; j0 += 4) {
+                        uint32_t xs[4], ps[4], rk[4];
+                        bool cand[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            xs[u] = w;
+                            ps[u] = 0;
+                            if (j0 + u < deg) {
+                                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&p.g.in_rec[eb + j0 + u]));
+                                xs[u] = raw.x;
+                                ps[u] = raw.w & 0xffu;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            cand[u] = false;
+                            rk[u] = 0;
+                            if (xs[u] != w) {
+                                const uint2 dx = cs_ld(&A.ds[xs[u]]);
+                                cand[u] = dx.x != CS_INF_BITS && dx.y > r;
+                                rk[u] = dx.y;
+                            }
+                        }
+                        uint32_t pm[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) pm[u] = cand[u] ? cs_ld(&A.predmask[rk[u]]) : 0u;
+                        double sx[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            cand[u] = cand[u] && ((pm[u] >> ps[u]) & 1u);  // x continues shortest paths through w (:861-866)
+                            sx[u] = cand[u] ? cs_ld(&A.sigma[rk[u]]) : 1.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (cand[u]) {
+                                const double f = (sx[u] == sigma_w) ? 1.0 : sigma_w / sx[u];
+                                const double* dxp = A.dep + (size_t)rk[u] * D2;
 #pragma unroll
                                 for (int i = 0; i < DT; ++i) {
                                     if (i < D) {
-                                        acc[i] += f * cs_ld(&dx[i]);
-                                        accb[i] += f * cs_ld(&dx[D + i]);
+                                        acc[i] += f * cs_ld(&dxp[i]);
+                                        accb[i] += f * cs_ld(&dxp[D + i]);
                                     }
                                 }
                             }
-                            const bool is_src = (w == src);
-                            const double pc = is_src ? 0.0 : p.od_off ? cs_ld(&odw[r]) : (__ldg(&p.eligible[w]) ? 0.5 : 1.0);
-                            double* dr = A.dep + (size_t)r * D2;
-#pragma unroll
-                            for (int i = 0; i < DT; ++i) {
-                                if (i < D) {
-                                    double seed = 0.0, seedb = 0.0;
-                                    if (!is_src && cost_w <= p.dist_f[i]) {
-                                        seed = pc;
-                                        seedb = pc * exp(-p.beta_d[i] * (double)cost_w);
-                                    }
-                                    const double dpn = seed + acc[i], dpb = seedb + accb[i];
-                                    cs_st(&dr[i], dpn);
-                                    cs_st(&dr[D + i], dpb);
-                                    if (!is_src) {
-                                        const double credit = dpn - seed, creditb = dpb - seedb;
-                                        if (credit > 0.0 || creditb > 0.0) {
-                                            ++n_ci;
-                                            if (credit > 0.0) cr[2 * i] = credit * wt_d;
-                                            if (creditb > 0.0) cr[2 * i + 1] = creditb * wt_d;
-                                        }
-                                    }
-                                }
-                            }
-                            cs_st(&A.bdone[r], (uint8_t)1);
-                            pending = false;
                         }
                     }
-                    __syncwarp();
-                    if (!__any_sync(CS_FULL, pending)) break;
+                    const bool is_src = (w == src);
+                    const double pc = is_src ? 0.0 : p.od_off ? cs_ld(&odw[r]) : (__ldg(&p.eligible[w]) ? 0.5 : 1.0);
+                    double* dr = A.dep + (size_t)r * D2;
+#pragma unroll
+                    for (int i = 0; i < DT; ++i) {
+                        if (i < D) {
+                            double seed = 0.0, seedb = 0.0;
+                            if (!is_src && cost_w <= p.dist_f[i]) {
+                                seed = pc;
+                                seedb = pc * exp(-p.beta_d[i] * (double)cost_w);
+                            }
+                            const double dpn = seed + acc[i], dpb = seedb + accb[i];
+                            cs_st(&dr[i], dpn);
+                            cs_st(&dr[D + i], dpb);
+                            if (!is_src) {
+                                const double credit = dpn - seed, creditb = dpb - seedb;
+                                if (credit > 0.0 || creditb > 0.0) {
+                                    ++n_ci;
+                                    if (credit > 0.0) cr[2 * i] = credit * wt_d;
+                                    if (creditb > 0.0) cr[2 * i + 1] = creditb * wt_d;
+                                }
+                            }
+                        }
+                    }
                 }
+                __syncwarp();
                 // packed credit scatter: 32/LPB nodes per warp instruction, LPB consecutive doubles each
                 {
                     constexpr int NQB = 2 * DT;
                     constexpr int LPB = NQB <= 2 ? 2 : NQB <= 4 ? 4 : NQB <= 8 ? 8 : NQB <= 16 ? 16 : 32;
                     constexpr int GB = 32 / LPB;
                     const int q = (int)(lane & (LPB - 1));
-                    const uint32_t cnt = min(32u, R - (uint32_t)b0);
                     for (uint32_t g0 = 0; g0 < cnt; g0 += GB) {
                         const int sl = (int)(g0 + lane / LPB);
                         const uint32_t nd = __shfl_sync(CS_FULL, w, sl);
@@ -408,6 +441,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
                         if (v > 0.0) cs_red_add(p.acc_b + (size_t)nd * p.bw + q, v);
                     }
                 }
+                hi -= (int)cnt;
             }
         }
 

@@ -164,25 +164,13 @@ __device__ __forceinline__ CsView cs3_view(const CsV3Graph& g, const CsSrc3& S, 
 // The seconds of a chain (both directions, <= cs3_pb(CS3_KMAX) + CS3_KMAX + 1 = 29 floats) are staged with independent
 // asynchronous 16-byte copies (LDGSTS.128, no registers) into the lane's column of 16-byte cells; the sequential f32 walks
 // then run at shared-memory latency instead of one dependent L2 round trip per piece.  Float i of the block sits in cell
-// i / 4 of the lane: cells[(i / 4) * 32 + lane], component i % 4.
-#ifndef CS3_STAGE16
-#define CS3_STAGE16 1
-#endif
+// i / 4 of the lane: cells[(i / 4) * 32 + lane], component i % 4.  (4-byte copies per float, round 1: -2.6 % on the bench.)
 __device__ __forceinline__ void cs3_load_block(const CsV3Graph& g, const CsView& V, float* cb, uint32_t first, uint32_t count) {
-#if CS3_STAGE16
     const uint32_t c0 = first >> 2, c1 = (first + count + 3u) >> 2;
     const float* src = g.csec + V.blk;
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(cb);
     for (uint32_t c = c0; c < c1; ++c)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + c * 512u), "l"(src + 4u * c) : "memory");
-#else
-    const float* src = g.csec + V.blk + first;
-    for (uint32_t i = 0; i < count; ++i) {
-        const uint32_t e = first + i;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(cb + (e >> 2) * 128u + (e & 3u));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + i) : "memory");
-    }
-#endif
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
