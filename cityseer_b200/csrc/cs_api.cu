@@ -566,6 +566,7 @@ static int ensure_arena(cs_graph* g, int kind, int D) {
     L.sigma = take((size_t)rcap * 8);
     L.dep = take((size_t)rcap * 2 * D * 8);
     L.bdone = take((size_t)rcap * 8);  // shortest: u8 flags; other kernels: 8-byte per-rank scratch
+    if (kind != 3) L.erank = take((size_t)rcap * 16);  // node-level kernels: CSR rows by settle rank
     if (kind == 3) {
         L.frank = take((size_t)rcap * CS3_MAX_LINKS * 16);  // chain kernel: per link {candidate, neighbour, id, far rank}
         L.needm = take((size_t)rcap * 4);                  // chain kernel: links whose far junction continues the path

@@ -55,6 +55,7 @@ static int ensure_replay_arena(cs_graph* g, int D) {
     L.sigma = take((size_t)rcap * 8);
     L.dep = take((size_t)rcap * 2 * D * 8);
     L.bdone = take((size_t)rcap * 8);
+    L.erank = take((size_t)rcap * 16);
     L.stride = align_up(off, 4096);
     L.rcap = rcap;
     L.qcap = qcap;

@@ -6,7 +6,7 @@
 #include "cs_common.cuh"
 
 struct CsArenaLayout {
-    size_t ds, node_list, qa, qb, far, s_node, s_agg, predmask, sigma, dep, bdone, frank, needm, jrank, stride;
+    size_t ds, node_list, qa, qb, far, s_node, s_agg, predmask, sigma, dep, bdone, frank, needm, jrank, erank, stride;
     uint32_t rcap, qcap;
 };
 
@@ -23,6 +23,7 @@ struct CsWarpArena {
     double* sigma;         // [rcap] per-rank f64
     double* dep;           // [rcap][2D] per-rank f64 vectors
     uint8_t* bdone;        // [rcap * 8] per-rank flags / scratch
+    uint4* erank;          // [rcap] node-level kernels: {in_off, in-degree, out_off, out-degree} of the node at each rank
     uint32_t rcap, qcap;
 };
 
@@ -44,6 +45,7 @@ __device__ __forceinline__ CsWarpArena cs_arena(uint8_t* arena, const CsArenaLay
     A.sigma = reinterpret_cast<double*>(base + L.sigma);
     A.dep = reinterpret_cast<double*>(base + L.dep);
     A.bdone = base + L.bdone;
+    A.erank = reinterpret_cast<uint4*>(base + L.erank);
     A.rcap = L.rcap;
     A.qcap = L.qcap;
     return A;
@@ -269,7 +271,12 @@ __device__ __forceinline__ void cs_p2_order(const CsGraphDev& g, const CsWarpAre
         cs_st(&A.sigma[rank], 0.0);
         cs_st(reinterpret_cast<unsigned long long*>(A.bdone) + rank, 0ull);
         cs_st(&minsucc_out[rank], CS_NOSLOT);
-        edge_iters += __ldg(&g.in_off[node + 1]) - __ldg(&g.in_off[node]);
+        // the CSR rows of the node, by rank: the later phases read them next to s_node / s_agg (one coalesced round trip)
+        // instead of chasing in_off[s_node[r]]
+        const uint32_t ib = __ldg(&g.in_off[node]), ie = __ldg(&g.in_off[node + 1]);
+        const uint32_t ob = __ldg(&g.out_off[node]), oe = __ldg(&g.out_off[node + 1]);
+        cs_st(&A.erank[rank], make_uint4(ib, ie - ib, ob, oe - ob));
+        edge_iters += ie - ib;
     }
     __syncwarp();
 }

@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
                 const float av = cs_ld(&A.s_agg[r]);
                 const float cost_v = __fmul_rn(av, p.speed);
                 if (p.closeness) atomicAdd(&histN[cs_first_threshold<DT>(p, cost_v)], 1u);
-                const uint32_t eb = __ldg(&p.g.out_off[v]);
-                const uint32_t deg = __ldg(&p.g.out_off[v + 1]) - eb;
+                const uint4 er = cs_ld(&A.erank[r]);
+                const uint32_t eb = er.z, deg = er.w;
                 // four out-edges at a time: the edge records, then the neighbours' map entries, are in flight together
                 for (uint32_t j0 = 0; j0 < deg; j0 += 4) {
                     uint4 raws[4];
@@ -329,24 +329,32 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
             int hi = (int)R - 1;
             while (hi >= 0) {
                 const int rr = hi - (int)lane;
-                const uint32_t ms = rr >= 0 ? cs_ld(&minsucc[rr]) : 0u;
+                // the chunk boundary (minsucc) and the per-rank state of the 32 candidates are loaded together: lanes
+                // beyond the boundary simply discard what they fetched
+                uint32_t ms = 0u, w = 0;
+                float agg_w = 0.f;
+                double sigma_w = 1.0;
+                uint4 er = make_uint4(0u, 0u, 0u, 0u);
+                if (rr >= 0) {
+                    ms = cs_ld(&minsucc[rr]);
+                    w = cs_ld(&A.s_node[rr]);
+                    agg_w = cs_ld(&A.s_agg[rr]);
+                    sigma_w = cs_ld(&A.sigma[rr]);
+                    er = cs_ld(&A.erank[rr]);
+                }
                 const uint32_t badm = __ballot_sync(CS_FULL, rr < 0 || ms <= (uint32_t)hi);
                 const uint32_t cnt = badm ? (uint32_t)__ffs(badm) - 1u : 32u;  // >= 1: minsucc[hi] > hi
                 const bool valid = lane < cnt;
                 const uint32_t r = (uint32_t)(hi - (int)lane);
-                uint32_t w = 0;
                 double cr[2 * DT];  // positive credits of this lane's node, slot 2 * i (plain) / 2 * i + 1 (beta-weighted)
 #pragma unroll
                 for (int q = 0; q < 2 * DT; ++q) cr[q] = 0.0;
                 if (valid) {
-                    w = cs_ld(&A.s_node[r]);
-                    const float cost_w = __fmul_rn(cs_ld(&A.s_agg[r]), p.speed);
-                    const double sigma_w = cs_ld(&A.sigma[r]);
+                    const float cost_w = __fmul_rn(agg_w, p.speed);
                     double acc[DT], accb[DT];
 #pragma unroll
                     for (int i = 0; i < DT; ++i) acc[i] = accb[i] = 0.0;
-                    const uint32_t eb = __ldg(&p.g.in_off[w]);
-                    const uint32_t deg = __ldg(&p.g.in_off[w + 1]) - eb;
+                    const uint32_t eb = er.x, deg = er.y;
                     // four in-edges at a time, each level of the dependent chain (edge record -> neighbour's map entry ->
                     // its predecessor mask -> its sigma) issued for the whole group before anything is consumed: the
                     // round trips overlap instead of adding up edge by edge

@@ -1000,23 +1000,28 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                 }
 #endif
                 const int rr = hi - (int)lane;
-                const uint32_t ms = rr >= 0 ? cs_ld(&minsucc[rr]) : 0u;
+                // the chunk boundary (minsucc) and the per-rank state of the 32 candidate junctions are loaded together;
+                // lanes beyond the boundary discard what they fetched
+                uint32_t ms = 0u, w = 0, off = 0, deg = 0, nm = 0;
+                float aw = 0.f;
+                double sigma_w = 1.0;
+                unsigned long long info8 = 0ull;
+                if (rr >= 0) {
+                    ms = cs_ld(&minsucc[rr]);
+                    w = cs_ld(&A.s_node[rr]);
+                    aw = cs_ld(&A.s_agg[rr]);
+                    sigma_w = cs_ld(&A.sigma[rr]);
+                    nm = cs_ld(&needm[rr]);
+                    const uint2 ji = cs_ld(&jrank[rr]);
+                    off = ji.x;
+                    deg = ji.y & 0xffu;
+                    info8 = cs_ld(reinterpret_cast<const unsigned long long*>(linfo + (size_t)rr * 8));
+                }
                 const uint32_t badm = __ballot_sync(CS_FULL, rr < 0 || ms <= (uint32_t)hi);
                 const uint32_t cnt = badm ? (uint32_t)__ffs(badm) - 1u : 32u;  // >= 1: minsucc[hi] > hi
                 const bool valid = lane < cnt;
                 const uint32_t r = (uint32_t)(hi - (int)lane);
-                uint32_t w = 0, off = 0, deg = 0, nm = 0;
-                float aw = 0.f;
-                double sigma_w = 1.0;
-                if (valid) {
-                    w = cs_ld(&A.s_node[r]);
-                    aw = cs_ld(&A.s_agg[r]);
-                    sigma_w = cs_ld(&A.sigma[r]);
-                    nm = cs_ld(&needm[r]);
-                    const uint2 ji = cs_ld(&jrank[r]);
-                    off = ji.x;
-                    deg = ji.y & 0xffu;
-                }
+                if (!valid) deg = 0;
                 uint32_t inc = deg;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -1026,7 +1031,6 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                 const uint32_t totalL = __shfl_sync(CS_FULL, inc, 31);
                 __syncwarp();
                 if (valid) {
-                    const unsigned long long info8 = cs_ld(reinterpret_cast<const unsigned long long*>(linfo + (size_t)r * 8));
                     *reinterpret_cast<unsigned long long*>(s_info + lane * 8) = info8;
                     for (uint32_t j = 0; j < deg; ++j) s_llist[inc - deg + j] = (uint16_t)(lane | (j << 5));
                 }
