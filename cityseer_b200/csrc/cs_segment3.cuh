@@ -461,9 +461,9 @@ __global__ void __launch_bounds__(cs3s_warps<DT>() * 32, 1) cs_k_segment3(const 
                     __syncwarp();
                     if (go) {
                         const float av = __uint_as_float(lavb);
+                        const uint2 dF = cs_ld(&A.ds[V.far]);  // issued before the staging wait: the round trips overlap
                         cs3_load_block(g, V, cblk, 0, V.nv);
                         const uint32_t k = V.k;
-                        const uint2 dF = cs_ld(&A.ds[V.far]);
                         const uint32_t fid = V.far == J ? S.id : V.far;
                         const bool f_reached = dF.x != INF;
                         float a = av;
@@ -679,6 +679,11 @@ __global__ void __launch_bounds__(cs3s_warps<DT>() * 32, 1) cs_k_segment3(const 
                     deg = ji.y & 0xffu;
                     info8 = cs_ld(reinterpret_cast<const unsigned long long*>(linfo + (size_t)rr * 8));
                 }
+                // ranks of the junctions at the far ends of the links, fetched with the rest of the per-rank state and handed
+                // to the link lanes by shuffles (one round trip to the far junction's subtree sum instead of two)
+                uint32_t frk[CS3_MAX_LINKS];
+#pragma unroll
+                for (int q = 0; q < (int)CS3_MAX_LINKS; ++q) frk[q] = (rr >= 0 && (uint32_t)q < deg) ? cs_ld(&cand[(size_t)rr * 8 + q].w) : 0u;
                 const uint32_t badm = __ballot_sync(CS_FULL, rr < 0 || ms <= (uint32_t)hi);
                 const uint32_t cnt = badm ? (uint32_t)__ffs(badm) - 1u : 32u;  // >= 1: minsucc[hi] > hi
                 const bool valid = lane < cnt;
@@ -709,6 +714,13 @@ __global__ void __launch_bounds__(cs3s_warps<DT>() * 32, 1) cs_k_segment3(const 
                     const float lol = __shfl_sync(CS_FULL, ol.x, jl);
                     const uint32_t lnm = __shfl_sync(CS_FULL, nm, jl);
                     const uint32_t lr = (uint32_t)(hi - (int)jl);
+                    uint32_t rankF = 0;
+#pragma unroll
+                    for (int q = 0; q < (int)CS3_MAX_LINKS; ++q) {
+                        const uint32_t t = __shfl_sync(CS_FULL, frk[q], jl);
+                        if ((uint32_t)q == j) rankF = t;
+                    }
+                    rankF &= 0x0fffffffu;
                     uint32_t T = 0;
                     bool work = false;
                     double dl[DT];  // subtree sum flowing toward the junction along this link
@@ -725,7 +737,6 @@ __global__ void __launch_bounds__(cs3s_warps<DT>() * 32, 1) cs_k_segment3(const 
                         if (work) V = cs3_view(g, S, lw, loff, j);
                         if (work && lr == 0) o_side = __ldg(&p.clen[V.blk + V.sv]);  // first piece from the source
                         if (needF) {
-                            const uint32_t rankF = cs_ld(&cand[(size_t)lr * 8 + j].w) & 0x0fffffffu;
                             const double* dx = dep + (size_t)rankF * D;
 #pragma unroll
                             for (int i = 0; i < DT; ++i)

@@ -696,9 +696,9 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                 const uint32_t lr = b0 + jl;
                 const float av = __uint_as_float(lavb);
                 const CsView V = cs3_view(g, S, lv, loff, j);
+                const uint2 dF = cs_ld(&A.ds[V.far]);  // issued before the staging wait: the two round trips overlap
                 cs3_load_block(g, V, cblk, 0, V.nv);
                 const uint32_t k = V.k;
-                const uint2 dF = cs_ld(&A.ds[V.far]);
                 const uint32_t fid = V.far == J ? S.id : V.far;
                 // Both waves at once: my front starts at v, theirs at F; the smaller front advances (the settle order of
                 // the chain's nodes), until the fronts meet or neither may advance (cutoff, centrality.rs:1407).  The owner
@@ -800,29 +800,38 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
             uint32_t pmask_c = 0;
             if (valid) {
                 const float av = __uint_as_float(avb);
-                for (uint32_t j = 0; j < deg; ++j) {
-                    const uint4 cd4 = cs_ld(&cand[(size_t)r * 8 + j]);
-                    const uint32_t ud = cd4.y;
-                    if (ud == INF) continue;
-                    const uint32_t uid = cd4.z & 0x0fffffffu, paf = cd4.z >> 28;
-                    int q = ncand++;
-                    while (q > 0) {
-                        const bool gt = cd[q - 1] != ud ? cd[q - 1] > ud
-                                        : cu[q - 1] != uid ? cs3_key(g, S, cu[q - 1]) > cs3_key(g, S, uid)
-                                                           : (cj[q - 1] >> 8) > paf;
-                        if (!gt) break;
-                        cc[q] = cc[q - 1];
-                        cu[q] = cu[q - 1];
-                        cd[q] = cd[q - 1];
-                        crk[q] = crk[q - 1];
-                        cj[q] = cj[q - 1];
-                        --q;
+                for (uint32_t j0 = 0; j0 < deg; j0 += 4) {
+                    // the records of four links are fetched together (independent addresses, one round trip per group)
+                    uint4 grp[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        grp[t] = j0 + t < deg ? cs_ld(&cand[(size_t)r * 8 + j0 + t]) : make_uint4(0u, INF, 0u, 0u);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint4 cd4 = grp[t];
+                        const uint32_t j = j0 + t;
+                        const uint32_t ud = cd4.y;
+                        if (ud == INF) continue;
+                        const uint32_t uid = cd4.z & 0x0fffffffu, paf = cd4.z >> 28;
+                        int q = ncand++;
+                        while (q > 0) {
+                            const bool gt = cd[q - 1] != ud ? cd[q - 1] > ud
+                                            : cu[q - 1] != uid ? cs3_key(g, S, cu[q - 1]) > cs3_key(g, S, uid)
+                                                               : (cj[q - 1] >> 8) > paf;
+                            if (!gt) break;
+                            cc[q] = cc[q - 1];
+                            cu[q] = cu[q - 1];
+                            cd[q] = cd[q - 1];
+                            crk[q] = crk[q - 1];
+                            cj[q] = cj[q - 1];
+                            --q;
+                        }
+                        cc[q] = __uint_as_float(cd4.x);
+                        cu[q] = uid;
+                        cd[q] = ud;
+                        crk[q] = cd4.w;
+                        cj[q] = j | (paf << 8);
                     }
-                    cc[q] = __uint_as_float(cd4.x);
-                    cu[q] = uid;
-                    cd[q] = ud;
-                    crk[q] = cd4.w;
-                    cj[q] = j | (paf << 8);
                 }
                 if (ncand == 1 && !p.phase2) {
                     pmask_c = 1u;
@@ -1017,6 +1026,12 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                     deg = ji.y & 0xffu;
                     info8 = cs_ld(reinterpret_cast<const unsigned long long*>(linfo + (size_t)rr * 8));
                 }
+                // ranks of the junctions at the far ends of this junction's links (left by the predecessor pass): fetched
+                // with the rest of the per-rank state and handed to the link lanes by shuffles, so that the far junctions'
+                // sigma / dependencies are one round trip away instead of two
+                uint32_t frk[CS3_MAX_LINKS];
+#pragma unroll
+                for (int q = 0; q < (int)CS3_MAX_LINKS; ++q) frk[q] = (rr >= 0 && (uint32_t)q < deg) ? cs_ld(&cand[(size_t)rr * 8 + q].w) : 0u;
                 const uint32_t badm = __ballot_sync(CS_FULL, rr < 0 || ms <= (uint32_t)hi);
                 const uint32_t cnt = badm ? (uint32_t)__ffs(badm) - 1u : 32u;  // >= 1: minsucc[hi] > hi
                 const bool valid = lane < cnt;
@@ -1047,7 +1062,12 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                     const float law = __shfl_sync(CS_FULL, aw, jl);
                     const double lsig = __shfl_sync(CS_FULL, sigma_w, jl);
                     const uint32_t lnm = __shfl_sync(CS_FULL, nm, jl);
-                    const uint32_t lr = (uint32_t)(hi - (int)jl);
+                    uint32_t rankF = 0;
+#pragma unroll
+                    for (int q = 0; q < (int)CS3_MAX_LINKS; ++q) {
+                        const uint32_t t = __shfl_sync(CS_FULL, frk[q], jl);
+                        if ((uint32_t)q == j) rankF = t;
+                    }
                     uint32_t T = 0;
                     bool tie2 = false, work = false;
                     double dl[DT], dlb[DT];  // dependency flowing toward the junction along this link
@@ -1065,7 +1085,6 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                         // F continues the path through this link iff F chose it as a predecessor (P3b left the bit)
                         const bool needF = (lnm >> j) & 1u;
                         work = T > 0 || needF || yhas;
-                        const uint32_t rankF = (needF || yhas || tie2) ? cs_ld(&cand[(size_t)lr * 8 + j].w) : 0u;
                         if (work) V = cs3_view(g, S, lw, loff, j);
                         const uint32_t k = V.k;
                         double sigma_F = 0.0;
