@@ -597,14 +597,21 @@ __global__ void __launch_bounds__(cs3s_warps<DT>() * 32, 1) cs_k_segment3(const 
             if (valid && r != 0) {
                 int nmatch = 0;
                 uint32_t pj = 0;
-                for (uint32_t j = 0; j < deg; ++j) {
-                    const uint4 c4 = cs_ld(&cand[(size_t)r * 8 + j]);
-                    if (c4.x != avb) continue;
-                    ++nmatch;
-                    prk = c4.w & 0x0fffffffu;
-                    pj = c4.w >> 28;
-                    first_len = __uint_as_float(c4.y);
-                    last_len = __uint_as_float(c4.z);
+                for (uint32_t j0 = 0; j0 < deg; j0 += 4) {  // four link records per round trip
+                    uint4 grp[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        grp[t] = j0 + t < deg ? cs_ld(&cand[(size_t)r * 8 + j0 + t]) : make_uint4(INF, 0u, 0u, 0u);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint4 c4 = grp[t];
+                        if (j0 + t >= deg || c4.x != avb) continue;
+                        ++nmatch;
+                        prk = c4.w & 0x0fffffffu;
+                        pj = c4.w >> 28;
+                        first_len = __uint_as_float(c4.y);
+                        last_len = __uint_as_float(c4.z);
+                    }
                 }
                 if (nmatch == 0) atomicCAS(p.error, 0, CS_ERR_ZERO_TIE);  // reached only through a zero-second tie
                 if (nmatch > 1) ambiguous = true;
@@ -679,11 +686,6 @@ __global__ void __launch_bounds__(cs3s_warps<DT>() * 32, 1) cs_k_segment3(const 
                     deg = ji.y & 0xffu;
                     info8 = cs_ld(reinterpret_cast<const unsigned long long*>(linfo + (size_t)rr * 8));
                 }
-                // ranks of the junctions at the far ends of the links, fetched with the rest of the per-rank state and handed
-                // to the link lanes by shuffles (one round trip to the far junction's subtree sum instead of two)
-                uint32_t frk[CS3_MAX_LINKS];
-#pragma unroll
-                for (int q = 0; q < (int)CS3_MAX_LINKS; ++q) frk[q] = (rr >= 0 && (uint32_t)q < deg) ? cs_ld(&cand[(size_t)rr * 8 + q].w) : 0u;
                 const uint32_t badm = __ballot_sync(CS_FULL, rr < 0 || ms <= (uint32_t)hi);
                 const uint32_t cnt = badm ? (uint32_t)__ffs(badm) - 1u : 32u;  // >= 1: minsucc[hi] > hi
                 const bool valid = lane < cnt;
@@ -714,13 +716,6 @@ __global__ void __launch_bounds__(cs3s_warps<DT>() * 32, 1) cs_k_segment3(const 
                     const float lol = __shfl_sync(CS_FULL, ol.x, jl);
                     const uint32_t lnm = __shfl_sync(CS_FULL, nm, jl);
                     const uint32_t lr = (uint32_t)(hi - (int)jl);
-                    uint32_t rankF = 0;
-#pragma unroll
-                    for (int q = 0; q < (int)CS3_MAX_LINKS; ++q) {
-                        const uint32_t t = __shfl_sync(CS_FULL, frk[q], jl);
-                        if ((uint32_t)q == j) rankF = t;
-                    }
-                    rankF &= 0x0fffffffu;
                     uint32_t T = 0;
                     bool work = false;
                     double dl[DT];  // subtree sum flowing toward the junction along this link
@@ -737,6 +732,7 @@ __global__ void __launch_bounds__(cs3s_warps<DT>() * 32, 1) cs_k_segment3(const 
                         if (work) V = cs3_view(g, S, lw, loff, j);
                         if (work && lr == 0) o_side = __ldg(&p.clen[V.blk + V.sv]);  // first piece from the source
                         if (needF) {
+                            const uint32_t rankF = cs_ld(&cand[(size_t)lr * 8 + j].w) & 0x0fffffffu;
                             const double* dx = dep + (size_t)rankF * D;
 #pragma unroll
                             for (int i = 0; i < DT; ++i)

@@ -1026,12 +1026,6 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                     deg = ji.y & 0xffu;
                     info8 = cs_ld(reinterpret_cast<const unsigned long long*>(linfo + (size_t)rr * 8));
                 }
-                // ranks of the junctions at the far ends of this junction's links (left by the predecessor pass): fetched
-                // with the rest of the per-rank state and handed to the link lanes by shuffles, so that the far junctions'
-                // sigma / dependencies are one round trip away instead of two
-                uint32_t frk[CS3_MAX_LINKS];
-#pragma unroll
-                for (int q = 0; q < (int)CS3_MAX_LINKS; ++q) frk[q] = (rr >= 0 && (uint32_t)q < deg) ? cs_ld(&cand[(size_t)rr * 8 + q].w) : 0u;
                 const uint32_t badm = __ballot_sync(CS_FULL, rr < 0 || ms <= (uint32_t)hi);
                 const uint32_t cnt = badm ? (uint32_t)__ffs(badm) - 1u : 32u;  // >= 1: minsucc[hi] > hi
                 const bool valid = lane < cnt;
@@ -1062,12 +1056,7 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                     const float law = __shfl_sync(CS_FULL, aw, jl);
                     const double lsig = __shfl_sync(CS_FULL, sigma_w, jl);
                     const uint32_t lnm = __shfl_sync(CS_FULL, nm, jl);
-                    uint32_t rankF = 0;
-#pragma unroll
-                    for (int q = 0; q < (int)CS3_MAX_LINKS; ++q) {
-                        const uint32_t t = __shfl_sync(CS_FULL, frk[q], jl);
-                        if ((uint32_t)q == j) rankF = t;
-                    }
+                    const uint32_t lr = (uint32_t)(hi - (int)jl);
                     uint32_t T = 0;
                     bool tie2 = false, work = false;
                     double dl[DT], dlb[DT];  // dependency flowing toward the junction along this link
@@ -1087,6 +1076,7 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                         work = T > 0 || needF || yhas;
                         if (work) V = cs3_view(g, S, lw, loff, j);
                         const uint32_t k = V.k;
+                        const uint32_t rankF = (needF || yhas || tie2) ? cs_ld(&cand[(size_t)lr * 8 + j].w) : 0u;
                         double sigma_F = 0.0;
                         if (needF || yhas || tie2) sigma_F = cs_ld(&A.sigma[rankF]);
                         if (needF) {
