@@ -1144,50 +1144,52 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                             }
                         }
                         __syncwarp();
-                        // seeds, one lane per node (centrality.rs:1802-1806)
-                        for (uint32_t e0 = 0; e0 < total; e0 += 32) {
-                            const uint32_t en = e0 + lane;
-                            if (en < total) {
-                                const float cost = s_cst[en];
-                                const uint32_t nid = s_ids[en];
-                                const double pc = __ldg(&p.eligible[nid]) ? 0.5 : 1.0;
-                                s_pcs[en] = (float)pc;
-                                if (p.closeness) {
-                                    // the closeness terms of the same node (P4 leaves the interiors to this pass when both
-                                    // metric families run): centrality.rs:1755-1777, f32 terms
-                                    double* base = p.acc_c + nid;
-                                    const double far_t = (double)__fmul_rn(cost, wt);
-                                    const double harm_t = (double)__fmul_rn(__fdiv_rn(1.0f, cost), wt);
+                        // seeds, one lane per node (centrality.rs:1802-1806).  (Two nodes per lane and iteration, to give the
+                        // scheduler independent instruction streams, cost 9 % on the bench: register pressure.)
+                        auto seed_node = [&](const uint32_t en) {
+                            const float cost = s_cst[en];
+                            const uint32_t nid = s_ids[en];
+                            const double pc = __ldg(&p.eligible[nid]) ? 0.5 : 1.0;
+                            s_pcs[en] = (float)pc;
+                            if (p.closeness) {
+                                // the closeness terms of the same node (P4 leaves the interiors to this pass when both
+                                // metric families run): centrality.rs:1755-1777, f32 terms
+                                double* base = p.acc_c + nid;
+                                const double far_t = (double)__fmul_rn(cost, wt);
+                                const double harm_t = (double)__fmul_rn(__fdiv_rn(1.0f, cost), wt);
 #pragma unroll
-                                    for (int i = 0; i < DT; ++i) {
-                                        if (i < D && cost <= p.dist_f[i]) {
-                                            ++n_ri;
-                                            double* q = base + (size_t)(5 * i) * g.n;
-                                            cs_red_add(q, (double)wt);
-                                            cs_red_add(q + g.n, far_t);
-                                            cs_red_add(q + 2 * (size_t)g.n, (double)__fmul_rn(rankf[i], cycles_wt));
-                                            cs_red_add(q + 3 * (size_t)g.n, harm_t);
-                                            cs_red_add(q + 4 * (size_t)g.n, (double)__fmul_rn(expf(__fmul_rn(-p.beta_f[i], cost)), wt));
-                                        }
+                                for (int i = 0; i < DT; ++i) {
+                                    if (i < D && cost <= p.dist_f[i]) {
+                                        ++n_ri;
+                                        double* q = base + (size_t)(5 * i) * g.n;
+                                        cs_red_add(q, (double)wt);
+                                        cs_red_add(q + g.n, far_t);
+                                        cs_red_add(q + 2 * (size_t)g.n, (double)__fmul_rn(rankf[i], cycles_wt));
+                                        cs_red_add(q + 3 * (size_t)g.n, harm_t);
+                                        cs_red_add(q + 4 * (size_t)g.n, (double)__fmul_rn(expf(__fmul_rn(-p.beta_f[i], cost)), wt));
                                     }
-                                }
-                                if (p.beta_chain) {
-                                    // beta_i = 2 * beta_{i+1} exactly (e.g. 500 / 1000 / 2000 m): exp(-beta_i c) is the square
-                                    // of exp(-beta_{i+1} c) to within an ulp or two
-                                    double ex = exp(-p.beta_d[D - 1] * (double)cost);
-#pragma unroll
-                                    for (int i = DT - 1; i >= 0; --i) {
-                                        if (i < D) {
-                                            s_crd[(2 * i + 1) * NB + en] = cost <= p.dist_f[i] ? pc * ex : 0.0;
-                                            ex *= ex;
-                                        }
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < DT; ++i)
-                                        if (i < D) s_crd[(2 * i + 1) * NB + en] = cost <= p.dist_f[i] ? pc * cs3_exp(-p.beta_d[i] * (double)cost) : 0.0;
                                 }
                             }
+                            if (p.beta_chain) {
+                                // beta_i = 2 * beta_{i+1} exactly (e.g. 500 / 1000 / 2000 m): exp(-beta_i c) is the square
+                                // of exp(-beta_{i+1} c) to within an ulp or two
+                                double ex = exp(-p.beta_d[D - 1] * (double)cost);
+#pragma unroll
+                                for (int i = DT - 1; i >= 0; --i) {
+                                    if (i < D) {
+                                        s_crd[(2 * i + 1) * NB + en] = cost <= p.dist_f[i] ? pc * ex : 0.0;
+                                        ex *= ex;
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < DT; ++i)
+                                    if (i < D) s_crd[(2 * i + 1) * NB + en] = cost <= p.dist_f[i] ? pc * cs3_exp(-p.beta_d[i] * (double)cost) : 0.0;
+                            }
+                        };
+                        for (uint32_t e0 = 0; e0 < total; e0 += 32) {
+                            const uint32_t en = e0 + lane;
+                            if (en < total) seed_node(en);
                         }
                         __syncwarp();
                         if (go) {
