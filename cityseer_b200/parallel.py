@@ -240,9 +240,9 @@ def centrality_shortest_sharded(ns, distances=None, betas=None, minutes=None, co
     speed = float(WALKING_SPEED if speed_m_s is None else np.float32(speed_m_s))
     tol = _c.validate_tolerance(tolerance)
     d, b, s = pair_distances_betas_time(speed, distances, betas, minutes, min_threshold_wt)
-    sources, wt, eligible, _n_prog, tracked, scale = ns._prepare_sources(sample_probability, None, None, source_indices)
     rank, ws = _dist_state(group)
-    src_block, wt_block = shard_sources(sources, wt, rank, ws)
+    src_block, wt_block, eligible, n_all, tracked, scale = ns._prepare_sources(sample_probability, None, None, source_indices,
+                                                                               shard=(rank, ws))  # fmt: skip
     dev = ns.device_graph()
     part = _partial_buffer((7, len(d), dev.node_bound), _device_of(dev))
     _o, st = _run_on_current_stream(dev, lambda: dev.centrality_shortest(
@@ -254,7 +254,7 @@ def centrality_shortest_sharded(ns, distances=None, betas=None, minutes=None, co
         host[5:7] *= scale
     res = _c.CentralityShortestResult(d, ns._node_keys_shared(), ns.frozen().node_indices, host, st)
     if tracked:
-        res.sampled_source_count = int(len(sources))
+        res.sampled_source_count = int(n_all) if source_indices is not None else 0
     return res
 
 
@@ -273,9 +273,9 @@ def centrality_simplest_sharded(ns, distances=None, betas=None, minutes=None, co
     unit = float(np.float32(180.0 if angular_scaling_unit is None else angular_scaling_unit))
     offset = float(np.float32(1.0 if farness_scaling_offset is None else farness_scaling_offset))
     d, _b, s = pair_distances_betas_time(speed, distances, betas, minutes, min_threshold_wt)
-    sources, wt, eligible, _n_prog, tracked, scale = ns._prepare_sources(sample_probability, None, None, source_indices)
     rank, ws = _dist_state(group)
-    src_block, wt_block = shard_sources(sources, wt, rank, ws)
+    src_block, wt_block, eligible, n_all, tracked, scale = ns._prepare_sources(sample_probability, None, None, source_indices,
+                                                                               shard=(rank, ws))  # fmt: skip
     dev = ns.device_graph()
     part = _partial_buffer((4, len(d), dev.node_bound), _device_of(dev))
     _o, st = _run_on_current_stream(dev, lambda: dev.centrality_simplest(
@@ -287,7 +287,7 @@ def centrality_simplest_sharded(ns, distances=None, betas=None, minutes=None, co
         host[3:4] *= scale
     res = _c.CentralitySimplestResult(d, ns._node_keys_shared(), ns.frozen().node_indices, host, st)
     if tracked:
-        res.sampled_source_count = int(len(sources))
+        res.sampled_source_count = int(n_all) if source_indices is not None else 0
     return res
 
 

@@ -709,8 +709,11 @@ class NetworkStructure:
         out[np.asarray(self.node_indices(), dtype=np.int64)] = w
         return out
 
-    def _prepare_sources(self, sample_probability, sampling_weights, random_seed, source_indices):
-        """Returns (sources u32[], wt f32[], eligible u8[node_bound], n_visited_for_progress, is_sampled, scale)
+    def _prepare_sources(self, sample_probability, sampling_weights, random_seed, source_indices, shard=None):
+        """``shard = (rank, world_size)``: return only that rank's contiguous block of the sources (and their weights);
+        ``eligible`` still describes the whole source set (it decides the pair counts 0.5 / 1.0, centrality.rs:1802-1806).
+
+        Returns (sources u32[], wt f32[], eligible u8[node_bound], n_visited_for_progress, is_sampled, scale)
         — prepare_source_sampling / sample_source_weight of centrality.rs:1032-1139.  A handful of numpy passes: this runs
         inside every timed call (a million-source plan costs a few milliseconds)."""
         f = self.frozen()
@@ -749,14 +752,19 @@ class NetworkStructure:
             sources = np.ascontiguousarray(src, dtype=np.uint32)
             eligible = np.zeros(nb, np.uint8)
             eligible[sources] = 1
+            n_all = len(sources)
+            if shard is not None:
+                from ..parallel import shard_bounds
+
+                lo_i, hi_i = shard_bounds(n_all, shard[0], shard[1])
+                sources = sources[lo_i:hi_i]
             wt = f.weight[sources]
             if sample_probability is not None and sample_probability != 1.0:
                 wt = (wt / np.float32(sample_probability)).astype(np.float32)
-            n_sources = len(sources)
             scale = 1.0
             if sample_probability is None:
-                scale = n_live / n_sources if n_sources else 1.0
-            return sources, np.ascontiguousarray(wt, dtype=np.float32), eligible, n_sources, True, scale
+                scale = n_live / n_all if n_all else 1.0
+            return np.ascontiguousarray(sources), np.ascontiguousarray(wt, dtype=np.float32), eligible, n_all, True, scale
         node_indices = f.node_indices
         live_mask = cache["live_mask"]
         eligible = cache["live_u8"].copy()
@@ -778,6 +786,11 @@ class NetworkStructure:
                 wt_all = (wt_all / ps).astype(np.float32)
         sources = np.ascontiguousarray(sources_all[keep], dtype=np.uint32)
         wt = np.ascontiguousarray(wt_all[keep], dtype=np.float32)
+        if shard is not None:
+            from ..parallel import shard_bounds
+
+            lo_i, hi_i = shard_bounds(len(sources), shard[0], shard[1])
+            sources, wt = np.ascontiguousarray(sources[lo_i:hi_i]), np.ascontiguousarray(wt[lo_i:hi_i])
         return sources, wt, eligible, n_sources, sample_probability is not None, 1.0
 
     # ------------------------------------------------------------------ compute entry points (CUDA only)

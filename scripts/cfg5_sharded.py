@@ -43,7 +43,8 @@ for km in a.km:
         rng = np.random.default_rng(7)
         kw = dict(source_indices=np.sort(rng.choice(N, a.sources, replace=False)), sample_probability=1.0)
         n_src = a.sources
-    parallel.centrality_shortest_sharded(ns, distances=d, source_indices=np.arange(0, N, max(1, N // 4096)), sample_probability=1.0)  # warm-up
+    for _ in range(2):  # warm-up: arena, page-locked result buffers (the merge alternates between two)
+        parallel.centrality_shortest_sharded(ns, distances=d, source_indices=np.arange(0, N, max(1, N // 4096)), sample_probability=1.0)
     torch.cuda.synchronize()
     if ws > 1:
         dist.barrier()
