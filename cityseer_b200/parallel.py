@@ -118,11 +118,7 @@ class _SharedHost:
         self.array = None
         try:
             self.shm.close()
-        except BufferError:
-            # result arrays handed out earlier still view the mapping: leave it to process exit
-            self.shm._mmap = None  # noqa: SLF001
-            self.shm._buf = None  # noqa: SLF001
-        except Exception:  # noqa: BLE001
+        except Exception:  # noqa: BLE001 - result arrays handed out earlier may still view the mapping: process exit frees it
             pass
 
 
