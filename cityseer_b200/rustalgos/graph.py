@@ -1012,16 +1012,22 @@ class NetworkStructure:
         speed = np.float32(speed_m_s)
         dev = self.device_graph()
         cap = int(capacity) if capacity else min(self.node_bound(), 16384)
+        src32 = src.astype(np.uint32)
         while True:
+            # a launch is bounded to 2^26 output entries (0.8 GB on the device); longer source lists go in slices
+            step = max(1, (1 << 26) // cap)
             try:
-                counts, order, pred, agg = dev.dijkstra_trees_shortest(src.astype(np.uint32), int(max_seconds), float(speed), cap)
+                parts = [dev.dijkstra_trees_shortest(src32[i : i + step], int(max_seconds), float(speed), cap)
+                         for i in range(0, max(len(src32), 1), step)]  # fmt: skip
                 break
             except ValueError as e:
                 if capacity or "output capacity" not in str(e) or cap >= self.node_bound():
                     raise
                 cap = min(self.node_bound(), cap * 4)
+        counts = np.concatenate([p[0] for p in parts])
         width = int(counts.max()) if len(counts) else 0
-        return counts, order[:, :width], pred[:, :width], agg[:, :width]
+        order, pred, agg = (np.concatenate([p[k][:, :width] for p in parts]) for k in (1, 2, 3))
+        return counts, order, pred, agg
 
     def dijkstra_tree_simplest(self, src_idx: int, max_seconds: int, speed_m_s: float):
         """centrality.rs:1510-1521"""

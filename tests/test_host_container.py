@@ -201,3 +201,58 @@ def test_od_matrix_semantics():
     with pytest.raises(OverflowError):
         OdMatrix([-1], [1], [1.0])
     assert OdMatrix([], [], []).len() == 0
+
+
+def test_frozen_columns_equal_the_payloads_after_mutations():
+    """frozen() copies the columnar mirror kept at mutation time: after adds, removals and slot reuse every column equals
+    what a walk over the payload objects gives (the reference's container is walked like that, graph.rs:384-391)."""
+    import math
+
+    _g, _n, _e, ns = H.primal_ns()
+    ns.remove_street_node(10)
+    s, e, k = ns.edge_references()[3]
+    ns.remove_street_edge(s, e, k)
+    ns.set_node_live(7, False)
+    new = ns.add_street_node("new", 123.0, 456.0, True, 2.5, z=7.0)
+    ns.add_street_edge(new, 0, 4, "new", "0", "LINESTRING (123 456, 200 456, 200 500)", imp_factor=1.5)
+    ns.add_transport_edge(0, new, 9, "0", "new", 33.0)
+    f = ns.frozen()
+    assert f.node_bound == ns.node_bound() and f.edge_bound == ns.edge_bound()
+    for i, p in enumerate(ns._nodes[: f.node_bound]):
+        assert f.node_exists[i] == (p is not None)
+        if p is None:
+            assert f.live[i] == 0 and f.weight[i] == 0 and math.isnan(f.z[i])
+            continue
+        assert (f.xs[i], f.ys[i]) == (p.x, p.y) and f.live[i] == p.live and f.weight[i] == np.float32(p.weight)
+        assert (math.isnan(f.z[i]) and p.z is None) or f.z[i] == p.z
+    for i, q in enumerate(ns._edges[: f.edge_bound]):
+        assert f.edge_exists[i] == (q is not None)
+        if q is None:
+            assert math.isnan(f.seconds[i]) and f.imp[i] == 1 and f.shared_key[i] == -1
+            continue
+        assert (f.src[i], f.dst[i], f.edge_idx[i], f.stamp[i]) == (q._src, q._dst, q.edge_idx, q._stamp)
+        assert f.imp[i] == np.float32(q.imp_factor)
+        for col, val in ((f.length, q.length), (f.angle_sum, q.angle_sum), (f.seconds, q.seconds)):
+            assert (math.isnan(col[i]) and math.isnan(val)) or col[i] == np.float32(val)
+    assert f.node_indices.tolist() == ns.node_indices()
+    # the transport edge: explicit seconds, NaN length (graph.rs:946-985)
+    t = int(np.flatnonzero(np.isfinite(f.seconds))[0])
+    assert f.seconds[t] == 33.0 and math.isnan(f.length[t]) and (f.src[t], f.dst[t]) == (0, new)
+    with pytest.raises(ValueError, match="Invalid seconds value"):
+        ns.add_transport_edge(0, new, 9, "0", "new", -1.0)
+    with pytest.raises(NotImplementedError):
+        ns.add_transport_node("stop", 0.0, 0.0)
+
+
+def test_sharded_source_plan_blocks_cover_the_plan():
+    """_prepare_sources(shard=(rank, ws)) returns that rank's contiguous block of the same plan; `eligible` always
+    describes the whole source set (it decides the pair counts, centrality.rs:1802-1806)."""
+    _g, _n, _e, ns = H.primal_ns()
+    ns.set_node_live(5, False)
+    for kw in ({"source_indices": None, "sample_probability": None}, {"source_indices": np.arange(3, 40, 2), "sample_probability": 0.5}):
+        full = ns._prepare_sources(kw["sample_probability"], None, 3, kw["source_indices"])
+        parts = [ns._prepare_sources(kw["sample_probability"], None, 3, kw["source_indices"], shard=(r, 3)) for r in range(3)]
+        assert np.concatenate([p[0] for p in parts]).tolist() == full[0].tolist()
+        assert np.allclose(np.concatenate([p[1] for p in parts]), full[1])
+        for p in parts:
+            assert np.array_equal(p[2], full[2]) and p[3] == full[3] and p[5] == full[5]
