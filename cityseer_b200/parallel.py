@@ -75,12 +75,22 @@ class _SharedHost:
         rank, ws = _dist_state(group)
         self.nbytes = int(nbytes)
         self._pinned_ptr = None
+        self.shm = None
+        self.array = None
+        self.owner = False
         name = [None]
-        if rank == 0:
-            self.shm = shared_memory.SharedMemory(create=True, size=max(self.nbytes, 8))
-            name[0] = self.shm.name
+        if rank == 0 and not os.environ.get("CITYSEER_B200_NO_SHM"):
+            try:  # tmpfs is sparse: check the room first, a full /dev/shm would only show as SIGBUS on first touch
+                st = os.statvfs("/dev/shm")
+                if st.f_bavail * st.f_frsize > 2 * self.nbytes + (64 << 20):
+                    self.shm = shared_memory.SharedMemory(create=True, size=max(self.nbytes, 8))
+                    name[0] = self.shm.name
+            except OSError:
+                self.shm = None
         if ws > 1:
             dist.broadcast_object_list(name, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        if name[0] is None:
+            return  # no room for a shared segment: merge_to_host falls back to all-reduce + one full download per rank
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=name[0])
             try:  # the creator unlinks; keep this process's resource tracker out of it
@@ -102,6 +112,8 @@ class _SharedHost:
             dist.barrier(group=group)
 
     def close(self):
+        if self.shm is None:
+            return
         try:
             if self._pinned_ptr is not None:
                 import torch
@@ -173,6 +185,18 @@ def merge_to_host(part, group=None) -> np.ndarray:
     chunk = (total + ws - 1) // ws
     flat = part.reshape(-1)
     on_gpu = part.is_cuda
+    buf = _shared_host(total * 8, group, pin=on_gpu)
+    if buf.array is None:
+        # no shared segment (tiny /dev/shm): every rank takes the whole sum - all-reduce, one full download per rank
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if on_gpu:
+            from . import _native
+
+            host = _native.pinned_empty(_native.load_library(), shape)
+        else:
+            host = np.empty(shape, np.float64)
+        torch.from_numpy(host).copy_(part)
+        return host
     if on_gpu and dist.get_backend(group) == "nccl":
         if chunk * ws != total:
             padded = torch.zeros(chunk * ws, dtype=part.dtype, device=part.device)
@@ -183,7 +207,6 @@ def merge_to_host(part, group=None) -> np.ndarray:
     else:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         mine = flat[rank * chunk : min(total, (rank + 1) * chunk)]
-    buf = _shared_host(total * 8, group, pin=on_gpu)
     host = buf.array.view(np.float64)
     lo, hi = rank * chunk, min(total, (rank + 1) * chunk)
     if hi > lo:

@@ -52,7 +52,13 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharded_sum_matches_single_rank(oracle_mod):
+@pytest.mark.parametrize("no_shm", [False, True], ids=["shared-buffer", "no-shm-fallback"])
+def test_two_rank_sharded_sum_matches_single_rank(oracle_mod, no_shm, monkeypatch):
+    # no_shm: the merge without a node-shared segment (a tiny /dev/shm): all-reduce + one full copy per rank
+    if no_shm:
+        monkeypatch.setenv("CITYSEER_B200_NO_SHM", "1")
+    else:
+        monkeypatch.delenv("CITYSEER_B200_NO_SHM", raising=False)
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
