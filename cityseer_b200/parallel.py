@@ -66,54 +66,65 @@ def sharded_sum(compute_shard: Callable[[np.ndarray, np.ndarray], "object"], sou
 
 # ---------------------------------------------------------------------------------------------- shared host result
 class _SharedHost:
-    """A host buffer shared by the ranks of one node (``/dev/shm``), page-locked in every rank that has a GPU."""
+    """A host buffer shared by the ranks of one node: a file in ``/dev/shm`` mapped by every rank (and page-locked in
+    every rank that has a GPU).  ``array`` is None when the node has no room for it."""
 
     def __init__(self, nbytes: int, group, pin: bool):
+        import mmap
+        import uuid
+
         import torch.distributed as dist
-        from multiprocessing import shared_memory
 
         rank, ws = _dist_state(group)
         self.nbytes = int(nbytes)
         self._pinned_ptr = None
-        self.shm = None
+        self._map = None
         self.array = None
+        self.path = None
         self.owner = False
+        size = max(self.nbytes, mmap.PAGESIZE)
         name = [None]
         if rank == 0 and not os.environ.get("CITYSEER_B200_NO_SHM"):
             try:  # tmpfs is sparse: check the room first, a full /dev/shm would only show as SIGBUS on first touch
                 st = os.statvfs("/dev/shm")
-                if st.f_bavail * st.f_frsize > 2 * self.nbytes + (64 << 20):
-                    self.shm = shared_memory.SharedMemory(create=True, size=max(self.nbytes, 8))
-                    name[0] = self.shm.name
+                if st.f_bavail * st.f_frsize > 2 * size + (64 << 20):
+                    path = f"/dev/shm/cityseer_b200_{os.getpid()}_{uuid.uuid4().hex[:12]}"
+                    fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                    try:
+                        os.ftruncate(fd, size)
+                        self._map = mmap.mmap(fd, size)
+                    finally:
+                        os.close(fd)
+                    name[0] = path
+                    self.owner = True
             except OSError:
-                self.shm = None
+                self._map = None
+                name[0] = None
         if ws > 1:
             dist.broadcast_object_list(name, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         if name[0] is None:
             return  # no room for a shared segment: merge_to_host falls back to all-reduce + one full download per rank
+        self.path = name[0]
         if rank != 0:
-            self.shm = shared_memory.SharedMemory(name=name[0])
-            try:  # the creator unlinks; keep this process's resource tracker out of it
-                from multiprocessing import resource_tracker
-
-                resource_tracker.unregister(self.shm._name, "shared_memory")  # noqa: SLF001
-            except Exception:  # noqa: BLE001
-                pass
-        self.owner = rank == 0
-        self.array = np.frombuffer(self.shm.buf, dtype=np.uint8, count=self.nbytes)
+            fd = os.open(self.path, os.O_RDWR)
+            try:
+                self._map = mmap.mmap(fd, size)
+            finally:
+                os.close(fd)
+        self.array = np.frombuffer(self._map, dtype=np.uint8, count=self.nbytes)
         if pin:
             import torch
 
             ptr = self.array.ctypes.data
-            err = torch.cuda.cudart().cudaHostRegister(ptr, max(self.nbytes, 8), 0)
+            err = torch.cuda.cudart().cudaHostRegister(ptr, size, 0)
             if int(err) == 0:
                 self._pinned_ptr = ptr
         if ws > 1:
-            dist.barrier(group=group)
+            dist.barrier(group=group)  # every rank has mapped the file
+        if self.owner:
+            os.unlink(self.path)  # the name goes away now; the pages live until the last mapping is dropped
 
     def close(self):
-        if self.shm is None:
-            return
         try:
             if self._pinned_ptr is not None:
                 import torch
@@ -122,16 +133,10 @@ class _SharedHost:
                 self._pinned_ptr = None
         except Exception:  # noqa: BLE001
             pass
-        if self.owner:
-            try:
-                self.shm.unlink()  # the name goes away now; the pages live until the last mapping is closed
-            except Exception:  # noqa: BLE001
-                pass
+        # result arrays handed out earlier may still view the mapping: dropping our references is enough, the mapping is
+        # released with the last of them (or at process exit)
         self.array = None
-        try:
-            self.shm.close()
-        except Exception:  # noqa: BLE001 - result arrays handed out earlier may still view the mapping: process exit frees it
-            pass
+        self._map = None
 
 
 _shared_cache: dict[tuple, _SharedHost] = {}
