@@ -106,6 +106,11 @@ struct cs_graph {
     uint32_t* d_od_dst = nullptr;
     float* d_od_w = nullptr;
     size_t od_off_cap = 0, od_pairs_cap = 0;
+    // the same lists for the chain-contracted kernel: destinations in its node numbering, ascending per origin
+    uint32_t* d3_od_dst = nullptr;
+    float* d3_od_w = nullptr;
+    size_t od3_pairs_cap = 0;
+    std::vector<uint32_t> h3_new_of_orig;
     int last_kernel = 1;
     int last_herr = 0;   // device error code of the last call (finish_call)
     int opt_kernel = 0;  // 0 auto (chain-contracted kernel when the graph qualifies, else the global-arena kernel),
@@ -455,7 +460,8 @@ extern "C" void cs_graph_destroy(cs_graph* g) {
                     (void*)g->d_error, (void*)g->d_out, (void*)g->d_arena, (void*)g->d_acc, (void*)g->d3_jinfo,
                     (void*)g->d3_links, (void*)g->d3_ctab, (void*)g->d3_cnum, (void*)g->d3_csec, (void*)g->d3_weight,
                     (void*)g->d3_int_chain, (void*)g->d3_orig_of_new, (void*)g->d3_new_of_orig, (void*)g->d3_eligible,
-                    (void*)g->d_od_off, (void*)g->d_od_dst, (void*)g->d_od_w, (void*)g->d_redo, (void*)g->d3_clen,
+                    (void*)g->d_od_off, (void*)g->d_od_dst, (void*)g->d_od_w, (void*)g->d3_od_dst, (void*)g->d3_od_w,
+                    (void*)g->d_redo, (void*)g->d3_clen,
                     (void*)g->d3_cimp, (void*)g->d_arena2})
         if (p) cudaFree(p);
     if (g->h_progress) cudaFreeHost(g->h_progress);
@@ -817,26 +823,30 @@ static float default_delta(const cs_graph* g, float speed) {
 
 #include "cs_api_v3.inl"
 
-template <int DT>
+template <int DT, bool OD>
 static cudaError_t v3_launch_t(const CsShortest3Params& t, uint32_t workers, cudaStream_t st) {
     constexpr uint32_t smem = cs3_smem_bytes<DT>();
     constexpr uint32_t W = cs3_warps<DT>();
-    cudaError_t e = cudaFuncSetAttribute(cs_k_shortest3<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(cs_k_shortest3<DT, OD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(workers / W, (t.n_sources + W - 1) / W);
     if (grid == 0) return cudaSuccess;
-    cs_k_shortest3<DT><<<grid, W * 32, smem, st>>>(t);
+    cs_k_shortest3<DT, OD><<<grid, W * 32, smem, st>>>(t);
     return cudaGetLastError();
 }
-static cudaError_t v3_launch(const CsShortest3Params& t, uint32_t workers, cudaStream_t st) {
+template <bool OD>
+static cudaError_t v3_launch_od(const CsShortest3Params& t, uint32_t workers, cudaStream_t st) {
     switch (cs_shortest_dt(t.D)) {
-        case 1: return v3_launch_t<1>(t, workers, st);
-        case 2: return v3_launch_t<2>(t, workers, st);
-        case 3: return v3_launch_t<3>(t, workers, st);
-        case 4: return v3_launch_t<4>(t, workers, st);
-        case 8: return v3_launch_t<8>(t, workers, st);
-        default: return v3_launch_t<CS_MAX_THRESHOLDS>(t, workers, st);
+        case 1: return v3_launch_t<1, OD>(t, workers, st);
+        case 2: return v3_launch_t<2, OD>(t, workers, st);
+        case 3: return v3_launch_t<3, OD>(t, workers, st);
+        case 4: return v3_launch_t<4, OD>(t, workers, st);
+        case 8: return v3_launch_t<8, OD>(t, workers, st);
+        default: return v3_launch_t<CS_MAX_THRESHOLDS, OD>(t, workers, st);
     }
+}
+static cudaError_t v3_launch(const CsShortest3Params& t, uint32_t workers, cudaStream_t st) {
+    return t.od_off ? v3_launch_od<true>(t, workers, st) : v3_launch_od<false>(t, workers, st);
 }
 
 // ------------------------------------------------------------------------------------------------ shortest
@@ -955,7 +965,7 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
 
 
     // ---- chain-contracted kernel (cs_shortest3.cuh): junction-level search, chains walked in place
-    const bool dumping = dump_agg || dump_sigma || dump_npred || od_off;  // served by the arena kernel
+    const bool dumping = dump_agg || dump_sigma || dump_npred;  // served by the arena kernel
     // auto: the chain-contracted kernel pays off when most nodes are chain interiors (decomposed / OSM-like graphs:
     // cfg #4 1.07 M vs 0.47 M sources/s); on a graph of junctions only the arena kernel is the faster one (cfg #2:
     // 3.7 M vs 2.1 M sources/s)
@@ -966,6 +976,8 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
                        "with more than %d links)", CS3_MAX_LINKS);
     g->last_kernel = 1;
     if (use_v3) {
+        std::vector<uint32_t> dst3;  // OD lists in the contracted numbering: alive until the stream is synchronised below
+        std::vector<float> w3;
         if (ensure_arena(g, 3, D)) return 1;
         if (g->cached_speed3 != speed && g->v3_ncsec) {
             cs_k_prep_csec<<<(int)((g->v3_ncsec + 255) / 256), 256, 0, g->stream>>>(g->d3_csec, g->d3_cnum, g->v3_ncsec, speed);
@@ -1004,6 +1016,42 @@ static int run_shortest(cs_graph* g, int D, const uint32_t* distances, const flo
         t.src_wt = g->d_src_wt;
         t.n_sources = n_sources;
         t.eligible = g->d3_eligible;
+        if (od_off) {
+            // the kernel looks a reached node up in its origin's destinations by binary search: translate them to the
+            // contracted copy's numbering and sort each origin's slice (destinations are unique per origin)
+            const size_t n_pairs = (size_t)od_off[n_sources];
+            if (g->od3_pairs_cap < std::max<size_t>(n_pairs, 1)) {
+                if (g->d3_od_dst) cudaFree(g->d3_od_dst);
+                if (g->d3_od_w) cudaFree(g->d3_od_w);
+                g->d3_od_dst = nullptr;
+                g->d3_od_w = nullptr;
+                g->od3_pairs_cap = 0;
+                CS_CUDA(cudaMalloc(&g->d3_od_dst, std::max<size_t>(n_pairs, 1) * 4));
+                CS_CUDA(cudaMalloc(&g->d3_od_w, std::max<size_t>(n_pairs, 1) * 4));
+                g->od3_pairs_cap = std::max<size_t>(n_pairs, 1);
+            }
+            std::vector<std::pair<uint32_t, float>> slice;
+            dst3.resize(n_pairs);
+            w3.resize(n_pairs);
+            for (uint64_t k = 0; k < n_sources; ++k) {
+                const size_t a = (size_t)od_off[k], b = (size_t)od_off[k + 1];
+                slice.clear();
+                for (size_t j = a; j < b; ++j) slice.emplace_back(g->h3_new_of_orig[od_dst[j]], od_w[j]);
+                std::sort(slice.begin(), slice.end(),
+                          [](const std::pair<uint32_t, float>& x, const std::pair<uint32_t, float>& y) { return x.first < y.first; });
+                for (size_t j = a; j < b; ++j) {
+                    dst3[j] = slice[j - a].first;
+                    w3[j] = slice[j - a].second;
+                }
+            }
+            if (n_pairs) {
+                CS_CUDA(cudaMemcpyAsync(g->d3_od_dst, dst3.data(), n_pairs * 4, cudaMemcpyHostToDevice, g->stream));
+                CS_CUDA(cudaMemcpyAsync(g->d3_od_w, w3.data(), n_pairs * 4, cudaMemcpyHostToDevice, g->stream));
+            }
+            t.od_off = g->d_od_off;
+            t.od_dst = g->d3_od_dst;
+            t.od_w = g->d3_od_w;
+        }
         t.acc_c = g->d_acc;
         t.acc_b = g->d_acc + (size_t)g->n * 5 * D;
         t.counters = g->d_counters;
@@ -1077,7 +1125,9 @@ extern "C" int cs_betweenness_od_shortest(cs_graph* g, int D, const uint32_t* di
         const int rc = run_shortest(g, D, distances, betas, seconds, speed_m_s, tolerance, 0, 1, n_sources, sources,
                                     ones.data(), nullptr, out, out_on_device, 0, stats, nullptr, nullptr, nullptr, od_off,
                                     od_dst, od_w);
-        if (!rc || !g || !grow_after_overflow(g, g->n, g->lay.rcap)) return rc;
+        if (!rc || !g) return rc;
+        const size_t nstates = g->last_kernel == 3 ? (size_t)g->v3_J + 1 : g->n;
+        if (!grow_after_overflow(g, nstates, g->lay.rcap)) return rc;
     }
 }
 

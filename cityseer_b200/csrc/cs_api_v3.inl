@@ -390,6 +390,7 @@ static int build_v3_graph(cs_graph* g, uint32_t n, const uint8_t* node_exists, c
     rc |= upload(&g->d3_weight, weight3);
     if (rc) return 1;
     CS_CUDA(cudaMalloc(&g->d3_eligible, n));
+    g->h3_new_of_orig = new_of_orig;
     g->v3_J = J;
     g->v3_I = I;
     g->v3_ncsec = cnum.size();

@@ -76,6 +76,11 @@ struct CsShortest3Params {
     const float* src_wt;
     unsigned long long n_sources;
     const uint8_t* eligible;  // by new id
+    // betweenness_od_shortest (centrality.rs:2419-2540): the dependency seeds are the OD weights of sources[k]'s
+    // destinations, od_dst / od_w [od_off[k], od_off[k + 1]) with od_dst in NEW ids, ascending per origin; NULL otherwise
+    const unsigned long long* od_off;
+    const uint32_t* od_dst;
+    const float* od_w;
     double* acc_c;            // [5 * D][n] metric-major by new id: row 5 * i + m
     double* acc_b;            // [2 * D][n] metric-major by new id: row 2 * i (plain) / 2 * i + 1 (beta-weighted)
     unsigned long long* counters;
@@ -88,6 +93,22 @@ struct CsShortest3Params {
 // Per-chain seconds block (16-byte aligned): fwd[0..k], padding to a multiple of four floats, then bwdr[0..k] - both
 // direction arrays start on a 16-byte boundary, so a block is staged with 16-byte asynchronous copies.
 __host__ __device__ __forceinline__ uint32_t cs3_pb(uint32_t k) { return (k + 4u) & ~3u; }
+
+// Seed of a reached node (centrality.rs:1802-1806: half a pair when both ends are sources, a whole one otherwise); in an
+// OD call the weight of the (origin, node) trip, zero when there is none (:2498-2507) - a binary search of the origin's
+// ascending destination slice [lo, hi).
+template <bool OD>
+__device__ __forceinline__ double cs3_pc(const CsShortest3Params& p, unsigned long long lo, const unsigned long long hi,
+                                         const uint32_t nid) {
+    if (!OD) return __ldg(&p.eligible[nid]) ? 0.5 : 1.0;
+    unsigned long long top = hi;
+    while (lo < top) {
+        const unsigned long long mid = (lo + top) >> 1;
+        if (__ldg(&p.od_dst[mid]) < nid) lo = mid + 1;
+        else top = mid;
+    }
+    return lo < hi && __ldg(&p.od_dst[lo]) == nid ? (double)__ldg(&p.od_w[lo]) : 0.0;
+}
 
 struct CsView {
     uint32_t far, sv, sF, k, id1, paf, cnt;  // sv / sF: offsets of the outward steps inside the chain's block
@@ -260,7 +281,9 @@ __device__ __forceinline__ void cs3_emit_closeness(const CsShortest3Params& p, c
     }
 }
 
-template <int DT>
+// OD: the origin-destination variant (seeds looked up in the origin's trip list) is a separate instantiation, so that the
+// plain kernel - at its register limit - does not carry the lookup state.
+template <int DT, bool OD = false>
 __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs_k_shortest3(const CsShortest3Params p) {
     constexpr uint32_t WARPS = cs3_warps<DT>();
     // per-warp shared memory: region A (4 KB): P2 bins | P3 candidates | P4 staged (node, cost) list | P5 node ids / costs;
@@ -990,6 +1013,8 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
         // ids, metric-major rows); the link's outflow is added to its junction in link order.
         if (p.betweenness) {
             const double wt_d = (double)wt;
+            const unsigned long long od_lo = OD && run ? __ldg(&p.od_off[si]) : 0ull;
+            const unsigned long long od_hi = OD && run ? __ldg(&p.od_off[si + 1]) : 0ull;
             int hi = (int)R - 1;
             while (hi >= 0) {
                 ++n_chunks;
@@ -1097,7 +1122,7 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                             for (uint32_t t = 0; t < k - T; ++t) b = __fadd_rn(b, __ldg(&g.csec[V.blk + V.sF + t]));
                             const float cost_y = __fmul_rn(b, p.speed);
                             const uint32_t yid = V.id1 + V.step * (int)T;
-                            const double pc = __ldg(&p.eligible[yid]) ? 0.5 : 1.0;
+                            const double pc = cs3_pc<OD>(p, od_lo, od_hi, yid);
                             const double f = lsig / (sigma_F + lsig);
 #pragma unroll
                             for (int i = 0; i < DT; ++i) {
@@ -1149,8 +1174,8 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                         auto seed_node = [&](const uint32_t en) {
                             const float cost = s_cst[en];
                             const uint32_t nid = s_ids[en];
-                            const double pc = __ldg(&p.eligible[nid]) ? 0.5 : 1.0;
-                            s_pcs[en] = (float)pc;
+                            const double pc = cs3_pc<OD>(p, od_lo, od_hi, nid);
+                            s_pcs[en] = (float)pc;  // 0.5 / 1 or an f32 trip weight: exact
                             if (p.closeness) {
                                 // the closeness terms of the same node (P4 leaves the interiors to this pass when both
                                 // metric families run): centrality.rs:1755-1777, f32 terms
@@ -1274,7 +1299,7 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
                     const bool is_src = r == 0;
                     const uint32_t wid = w == J ? S.id : w;
                     const float cost_w = __fmul_rn(aw, p.speed);
-                    const double pc = is_src ? 0.0 : (__ldg(&p.eligible[wid]) ? 0.5 : 1.0);
+                    const double pc = is_src ? 0.0 : cs3_pc<OD>(p, od_lo, od_hi, wid);
                     double* dr = A.dep + (size_t)r * D2;
                     double* col = p.acc_b + wid;
 #pragma unroll

@@ -132,7 +132,7 @@ int cs_segment_centrality(cs_graph* g, int D, const uint32_t* distances, const f
  * by a source weight.  `sources` are the live origins with outbound trips; the destinations / weights of sources[k] are
  * od_dst / od_w [od_off[k], od_off[k + 1]) (destinations unique per origin, as the reference's HashMap makes them).
  * `out` uses the [7][D][node_bound] layout of cs_centrality_shortest; only rows 5 (betweenness) and 6 (betweenness_beta)
- * are populated. */
+ * are populated.  Served by the same kernel choice as cs_centrality_shortest (chain-contracted on decomposed graphs). */
 int cs_betweenness_od_shortest(cs_graph* g, int D, const uint32_t* distances, const float* betas, const uint32_t* seconds,
                                float speed_m_s, float tolerance, uint64_t n_sources, const uint32_t* sources,
                                const uint64_t* od_off, const uint32_t* od_dst, const float* od_w, double* out,
