@@ -323,11 +323,17 @@ class DeviceGraph:
         self._run(call, progress, n_prog, n_src)
         return out, self._stats(st, D)
 
-    def betweenness_od_shortest(self, d, b, s, speed, tol, sources, od_off, od_dst, od_w, progress, n_prog):
-        """Returns float64 [7][D][node_bound] (rows 5, 6 populated) and the device counters."""
+    def betweenness_od_shortest(self, d, b, s, speed, tol, sources, od_off, od_dst, od_w, progress, n_prog,
+                                out_device_ptr: int | None = None):  # fmt: skip
+        """Returns float64 [7][D][node_bound] (rows 5, 6 populated) and the device counters; with ``out_device_ptr`` the
+        result stays in that device buffer (the sharded call merges it there) and ``None`` is returned for the array."""
         D, da, ba, sa = self._thresholds(d, b, s)
         st = CsStats()
-        out = pinned_empty(self._lib, (7, D, self.node_bound))
+        if out_device_ptr is None:
+            out = pinned_empty(self._lib, (7, D, self.node_bound))
+            optr, on_dev = out.ctypes.data_as(C.c_void_p), 0
+        else:
+            out, optr, on_dev = None, C.c_void_p(int(out_device_ptr)), 1
         sources = np.ascontiguousarray(sources, np.uint32)
         od_off = np.ascontiguousarray(od_off, np.uint64)
         od_dst = np.ascontiguousarray(od_dst, np.uint32)
@@ -336,8 +342,8 @@ class DeviceGraph:
         def call():
             return self._lib.cs_betweenness_od_shortest(
                 self._h, D, _ptr(da, _u32p), _ptr(ba, _f32p), _ptr(sa, _u32p), speed, tol, len(sources),
-                _ptr(sources, _u32p), _ptr(od_off, _u64p), _ptr(od_dst, _u32p), _ptr(od_w, _f32p),
-                out.ctypes.data_as(C.c_void_p), 0, C.byref(st),
+                _ptr(sources, _u32p), _ptr(od_off, _u64p), _ptr(od_dst, _u32p), _ptr(od_w, _f32p), optr, on_dev,
+                C.byref(st),
             )  # fmt: skip
 
         self._run(call, progress, n_prog, len(sources))

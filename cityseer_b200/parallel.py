@@ -336,3 +336,26 @@ def segment_centrality_sharded(ns, distances=None, betas=None, minutes=None, com
         out_device_ptr=part.data_ptr()))  # fmt: skip
     host = merge_to_host(part, group)
     return _c.CentralitySegmentResult(d, ns._node_keys_shared(), f.node_indices, host, st)
+
+
+def betweenness_od_shortest_sharded(ns, od_matrix, distances=None, betas=None, minutes=None, min_threshold_wt=None,
+                                    speed_m_s=None, tolerance=None, group=None):  # fmt: skip
+    """``NetworkStructure.betweenness_od_shortest`` (centrality.rs:2419-2540) over all ranks: the origins with outbound
+    trips shard in contiguous blocks of about equal trip counts, every rank seeds its own origins' destinations, and
+    the betweenness rows are merged by the same sum as the other calls."""
+    from .rustalgos import WALKING_SPEED, pair_distances_betas_time
+    from .rustalgos import centrality as _c
+
+    if not isinstance(od_matrix, _c.OdMatrix):
+        raise TypeError("argument 'od_matrix': expected OdMatrix")
+    speed = float(WALKING_SPEED if speed_m_s is None else np.float32(speed_m_s))
+    tol = _c.validate_tolerance(tolerance)
+    d, b, s = pair_distances_betas_time(speed, distances, betas, minutes, min_threshold_wt)
+    rank, ws = _dist_state(group)
+    sources, od_off, od_dst, od_w = ns._prepare_od(od_matrix, shard=(rank, ws))
+    dev = ns.device_graph()
+    part = _partial_buffer((7, len(d), dev.node_bound), _device_of(dev))
+    _o, st = _run_on_current_stream(dev, lambda: dev.betweenness_od_shortest(
+        d, b, s, speed, tol, sources, od_off, od_dst, od_w, None, len(sources), out_device_ptr=part.data_ptr()))  # fmt: skip
+    host = merge_to_host(part, group)
+    return _c.BetweennessShortestResult(d, ns._node_keys_shared(), ns.frozen().node_indices, host, st)

@@ -841,6 +841,33 @@ class NetworkStructure:
             res.reachability_totals = [int(x) for x in stats["reach_totals"]] if compute_closeness else [0] * len(d)
         return res
 
+    def _prepare_od(self, od_matrix, shard=None):
+        """Flat trip lists of an OD call: the live origins with outbound trips in node order (the reference walks
+        ``node_indices`` and skips the rest, centrality.rs:2470-2481), per origin its ``(destination, weight)`` pairs with
+        CSR offsets.  ``shard=(rank, world_size)``: only this rank's contiguous block of the origins, cut so that the
+        blocks hold about the same number of trips."""
+        f = self.frozen()
+        live = f.live.astype(bool) & f.node_exists.astype(bool)
+        origins = [o for o in sorted(od_matrix.map) if 0 <= o < f.node_bound and live[o] and od_matrix.map[o]]
+        if shard is not None and origins:
+            rank, world_size = shard
+            ends = np.cumsum([len(od_matrix.map[o]) for o in origins])
+            cuts = np.searchsorted(ends, ends[-1] * np.arange(1, world_size) / world_size, side="left") + 1
+            cuts = np.concatenate([[0], np.minimum(cuts, len(origins)), [len(origins)]])
+            origins = origins[int(cuts[rank]):int(cuts[rank + 1])]
+        od_off = np.zeros(len(origins) + 1, np.uint64)
+        od_dst, od_w = [], []
+        for k, o in enumerate(origins):
+            dests = od_matrix.map[o]
+            od_dst.extend(dests.keys())
+            od_w.extend(dests.values())
+            od_off[k + 1] = len(od_dst)
+        od_dst = np.asarray(od_dst, np.int64)
+        if len(od_dst) and (od_dst.min() < 0 or od_dst.max() >= f.node_bound):
+            bad = int(od_dst[(od_dst < 0) | (od_dst >= f.node_bound)][0])
+            raise ValueError(f"OD destination {bad} is out of range for node_bound {f.node_bound}")
+        return np.asarray(origins, np.uint32), od_off, od_dst.astype(np.uint32), np.asarray(od_w, np.float32)
+
     def betweenness_od_shortest(
         self,
         od_matrix,
@@ -862,25 +889,12 @@ class NetworkStructure:
         d, b, s = pair_distances_betas_time(speed, distances, betas, minutes, min_threshold_wt)
         tol = _centrality.validate_tolerance(tolerance)
         f = self.frozen()
-        live = f.live.astype(bool) & f.node_exists.astype(bool)
-        sources, od_off, od_dst, od_w = [], [0], [], []
-        for src in f.node_indices.tolist():  # the reference iterates node_indices and skips the rest (:2470-2481)
-            dests = od_matrix.map.get(src)
-            if not live[src] or not dests:
-                continue
-            for dest, w in dests.items():
-                if dest >= f.node_bound:
-                    raise ValueError(f"OD destination {dest} is out of range for node_bound {f.node_bound}")
-                od_dst.append(dest)
-                od_w.append(w)
-            sources.append(src)
-            od_off.append(len(od_dst))
+        sources, od_off, od_dst, od_w = self._prepare_od(od_matrix)
         self.progress_init()
         dev = self.device_graph()
         out, stats = dev.betweenness_od_shortest(
-            d, b, s, speed, tol, np.asarray(sources, np.uint32), np.asarray(od_off, np.uint64),
-            np.asarray(od_dst, np.uint32), np.asarray(od_w, np.float32),
-            None if pbar_disabled else self._progress, len(f.node_indices),
+            d, b, s, speed, tol, sources, od_off, od_dst, od_w, None if pbar_disabled else self._progress,
+            len(f.node_indices),
         )  # fmt: skip
         return _centrality.BetweennessShortestResult(d, self._node_keys_shared(), f.node_indices, out, stats)
 

@@ -256,3 +256,34 @@ def test_sharded_source_plan_blocks_cover_the_plan():
         assert np.allclose(np.concatenate([p[1] for p in parts]), full[1])
         for p in parts:
             assert np.array_equal(p[2], full[2]) and p[3] == full[3] and p[5] == full[5]
+
+
+def test_od_lists_and_their_shards():
+    """_prepare_od: live origins with trips in node order, CSR offsets; the shards of a multi-rank call are contiguous,
+    disjoint, complete, and balanced by trip count."""
+    from cityseer_b200.rustalgos.centrality import OdMatrix
+
+    _g, _n, _e, ns = H.primal_ns()
+    idx = ns.node_indices()
+    rng = np.random.default_rng(2)
+    o = rng.choice(idx, 400).tolist() + [idx[3]] * 150  # one origin with many trips
+    t = rng.choice(idx, len(o)).tolist()
+    w = rng.uniform(0.1, 2.0, len(o)).tolist()
+    od = OdMatrix(o, t, w)
+    src, off, dst, wt = ns._prepare_od(od)
+    assert src.tolist() == sorted(od.map) and off[0] == 0 and off[-1] == len(dst) == od.len() == len(wt)
+    for k, origin in enumerate(src.tolist()):
+        a, b = int(off[k]), int(off[k + 1])
+        assert dict(zip(dst[a:b].tolist(), wt[a:b].tolist())) == {d: np.float32(x) for d, x in od.map[origin].items()}
+    for world in (1, 2, 3, 8):
+        parts = [ns._prepare_od(od, shard=(r, world)) for r in range(world)]
+        assert np.concatenate([p[0] for p in parts]).tolist() == src.tolist()
+        assert np.concatenate([p[2] for p in parts]).tolist() == dst.tolist()
+        assert all(p[1][0] == 0 and p[1][-1] == len(p[2]) and len(p[1]) == len(p[0]) + 1 for p in parts)
+        if world == 2:
+            assert abs(len(parts[0][2]) - len(parts[1][2])) <= max(len(x) for x in od.map.values())
+    with pytest.raises(ValueError, match="out of range"):
+        ns._prepare_od(OdMatrix([idx[0]], [10**6], [1.0]))
+    # a dead origin is skipped, like the reference's is_node_live check (centrality.rs:2473)
+    ns.set_node_live(idx[3], False)
+    assert idx[3] not in ns._prepare_od(od)[0].tolist()

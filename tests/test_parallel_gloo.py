@@ -23,6 +23,15 @@ def _free_port():
     return p
 
 
+def _od_matrix(ns):
+    from cityseer_b200.rustalgos.centrality import OdMatrix
+
+    idx = ns.node_indices()
+    rng = np.random.default_rng(17)
+    o = rng.choice(idx, 250)
+    return OdMatrix(o.tolist(), rng.choice(idx, 250).tolist(), rng.uniform(0.2, 3.0, 250).tolist())
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -47,7 +56,13 @@ def _worker(rank, world, port, q):
         merged.append(parallel.merge_to_host(part).copy())
     assert all(np.array_equal(m, merged[0]) for m in merged)
     assert np.array_equal(merged[0], total.numpy())
-    q.put((rank, total.numpy(), (lo, hi)))
+    # OD betweenness: each rank's block of the origins (cut by trip count), merged the same way
+    od = _od_matrix(ns)
+    src_b, off_b, dst_b, w_b = ns._prepare_od(od, shard=(rank, world))
+    od_part = np.zeros((7, len(d), f.node_bound))
+    od_part[5], od_part[6] = og.betweenness_od(d, b, s, H.SPEED, src_b.tolist(), off_b.tolist(), dst_b.tolist(), w_b.tolist())
+    od_merged = parallel.merge_to_host(torch.from_numpy(od_part)).copy()
+    q.put((rank, total.numpy(), (lo, hi), od_merged, len(src_b)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -75,9 +90,16 @@ def test_two_rank_sharded_sum_matches_single_rank(oracle_mod, no_shm, monkeypatc
     ref, _ = oracle_mod.OracleGraph(ns.frozen()).centrality_shortest(d, b, s, H.SPEED)
     bounds = sorted(x[2] for x in got)
     assert bounds[0][0] == 0 and bounds[0][1] == bounds[1][0] and bounds[1][1] == 57
-    for _rank, total, _b in got:
+    od = _od_matrix(ns)
+    src, off, dst, w = ns._prepare_od(od)
+    od_ref = oracle_mod.OracleGraph(ns.frozen()).betweenness_od(d, b, s, H.SPEED, src.tolist(), off.tolist(), dst.tolist(), w.tolist())
+    assert sum(x[4] for x in got) == len(src) and all(x[4] > 0 for x in got)
+    for _rank, total, _b, od_merged, _n in got:
         assert np.array_equal(total[0], ref[0]) and np.array_equal(total[2], ref[2])
         np.testing.assert_allclose(total, ref, rtol=1e-12, atol=1e-12)
+        assert od_merged[5].max() > 0 and np.all(od_merged[:5] == 0)
+        np.testing.assert_allclose(od_merged[5], od_ref[0], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(od_merged[6], od_ref[1], rtol=1e-12, atol=1e-12)
 
 
 def test_shard_bounds_cover_everything():
