@@ -44,7 +44,14 @@ enum { CS_C_SOURCES = 0, CS_C_SETTLED, CS_C_EDGE_ITERS, CS_C_SUM_RI, CS_C_SUM_CI
 
 enum { CS_ERR_NONE = 0, CS_ERR_REACH_OVERFLOW = 1, CS_ERR_QUEUE_OVERFLOW = 2, CS_ERR_PRED_OVERFLOW_ = 3, CS_ERR_ZERO_TIE = 4 };
 
-__device__ __forceinline__ uint32_t cs_lane() { return threadIdx.x & 31u; }
+// every kernel here is launched with a one-dimensional block of whole warps: %laneid == threadIdx.x & 31.  The special
+// register read is one instruction where the mask needs two, and the compiler re-reads it at most uses rather than
+// keeping a register (8 % of the arena kernel's instructions were this line, profiles/r02z_ncu_shortest_arena.txt)
+__device__ __forceinline__ uint32_t cs_lane() {
+    uint32_t l;
+    asm("mov.u32 %0, %%laneid;" : "=r"(l));
+    return l;
+}
 __device__ __forceinline__ uint32_t cs_lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
