@@ -52,6 +52,14 @@ __device__ __forceinline__ uint32_t cs_lane() {
     asm("mov.u32 %0, %%laneid;" : "=r"(l));
     return l;
 }
+// index of the warp inside its CTA, broadcast from lane 0 so that the compiler knows it is the same in every lane: what is
+// derived from it (the warp's shared-memory window, its arena base) can then live in uniform registers instead of
+// being recomputed from the thread index at every use
+__device__ __forceinline__ uint32_t cs_warp_in_cta() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); }
+// a value every lane holds alike (loaded from one address, read from a shared variable ...), restated as a broadcast from
+// lane 0: the compiler then knows it is warp-uniform and may keep it in a uniform register
+template <class T>
+__device__ __forceinline__ T cs_uni(T v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ uint32_t cs_lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

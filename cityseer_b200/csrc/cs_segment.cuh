@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(CS_SEG_WARPS * 32, CS_SEG_MIN_BLOCKS) cs_k_seg
     __shared__ unsigned long long s_base;
     __shared__ int s_err;
     const uint32_t lane = cs_lane();
-    const uint32_t wic = threadIdx.x >> 5;
+    const uint32_t wic = cs_warp_in_cta();
     const uint32_t worker = p.compact_arena ? blockIdx.x * p.src_per_cta + (wic < p.src_per_cta ? wic : 0u)
                                             : blockIdx.x * CS_SEG_WARPS + wic;
     uint32_t* bins = s_bins_all + (size_t)wic * CS_NBINS;

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(cs3s_warps<DT>() * 32, 1) cs_k_segment3(const 
 
     const uint32_t lane = cs_lane();
     const uint32_t ltmask = cs_lanemask_lt();
-    const uint32_t wic = threadIdx.x >> 5;
+    const uint32_t wic = cs_warp_in_cta();
     const uint32_t worker = blockIdx.x * WARPS + wic;
     uint8_t* s_warp = s_dyn + (size_t)wic * BYTES_W;
     uint32_t* bins = reinterpret_cast<uint32_t*>(s_warp);
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(cs3s_warps<DT>() * 32, 1) cs_k_segment3(const 
         bool run = si < p.n_sources;
         const uint32_t src_orig = run ? __ldg(&p.sources[si]) : 0u;
         CsSrc3 S;
-        S.id = run ? __ldg(&g.new_of_orig[src_orig]) : 0u;
+        S.id = run ? __ldg(&g.new_of_orig[src_orig]) : 0u;  // (cs_uni broadcasts of the per-source values: no gain here)
         S.interior = S.id >= J ? 1u : 0u;
         S.slot = S.interior ? J : S.id;
         S.soff = S.ibase = S.k = S.p = S.A = S.B = S.posA = S.posB = 0;

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
     __shared__ float s_rank_all[CS_WARPS_PER_CTA][CS_MAX_THRESHOLDS];
 
     const uint32_t lane = cs_lane();
-    const uint32_t wic = threadIdx.x >> 5;
+    const uint32_t wic = cs_warp_in_cta();
     const uint32_t worker = blockIdx.x * CS_WARPS_PER_CTA + wic;
     uint32_t* bins = s_bins_all[wic];
     uint32_t* histN = s_hist_all[wic][0];
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_MIN_BLOCKS) cs_k_sho
         si = __shfl_sync(CS_FULL, si, 0);
         if (si >= p.n_sources) break;
         if (*reinterpret_cast<volatile int*>(p.error) != 0) break;
-        const uint32_t src = __ldg(&p.sources[si]);
+        const uint32_t src = __ldg(&p.sources[si]);  // (broadcasting these as cs_uni values costs this kernel 5 %)
         const float wt = __ldg(&p.src_wt[si]);
 
         // ------------------------------------------------------------------ P1 + P2

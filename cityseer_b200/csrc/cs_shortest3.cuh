@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
 
     const uint32_t lane = cs_lane();
     const uint32_t ltmask = cs_lanemask_lt();
-    const uint32_t wic = threadIdx.x >> 5;
+    const uint32_t wic = cs_warp_in_cta();
     const uint32_t worker = blockIdx.x * WARPS + wic;
     uint8_t* s_warp = s_dyn + (size_t)wic * BYTES_W;
     uint32_t* bins = reinterpret_cast<uint32_t*>(s_warp);
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
         }
         __syncthreads();
         if (s_base >= p.n_sources || s_err != 0) break;
-        const unsigned long long si = s_base + wic;
+        const unsigned long long si = cs_uni(s_base) + wic;
         bool run = si < p.n_sources;
 #define CS3_BAR() __syncthreads()
 #else
@@ -368,22 +368,22 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
         bool run = true;
 #define CS3_BAR()
 #endif
-        const float wt = run ? __ldg(&p.src_wt[si]) : 0.f;
+        const float wt = cs_uni(run ? __ldg(&p.src_wt[si]) : 0.f);
         CsSrc3 S;
-        S.id = run ? __ldg(&g.new_of_orig[__ldg(&p.sources[si])]) : 0u;
+        S.id = cs_uni(run ? __ldg(&g.new_of_orig[__ldg(&p.sources[si])]) : 0u);  // per-source values: warp-uniform
         S.interior = S.id >= J ? 1u : 0u;
         S.slot = S.interior ? J : S.id;
         S.soff = S.ibase = S.k = S.p = S.A = S.B = S.posA = S.posB = 0;
         if (S.interior) {
             const uint32_t c = __ldg(&g.int_chain[S.id - J]);
             const uint4 c0 = __ldg(&g.ctab[2 * c]), c1 = __ldg(&g.ctab[2 * c + 1]);
-            S.soff = c0.x;
-            S.ibase = c0.y;
-            S.k = c0.z;
-            S.A = c0.w;
-            S.B = c1.x;
-            S.posA = c1.y;
-            S.posB = c1.z;
+            S.soff = cs_uni(c0.x);
+            S.ibase = cs_uni(c0.y);
+            S.k = cs_uni(c0.z);
+            S.A = cs_uni(c0.w);
+            S.B = cs_uni(c1.x);
+            S.posA = cs_uni(c1.y);
+            S.posB = cs_uni(c1.z);
             S.p = S.id - J - S.ibase + 1;
         }
         long long tc[7];
@@ -553,6 +553,7 @@ __global__ void __launch_bounds__(cs3_warps<DT>() * 32, cs3_min_blocks<DT>()) cs
 #endif
         }
         if (!run) R = 0;  // an idle warp still meets the barriers; every loop below is empty for it
+        R = cs_uni(R);
         CS3_BAR();
 
         // ------------------------------------------------------------------ P2: exact settle order of the junctions

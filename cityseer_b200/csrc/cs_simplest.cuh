@@ -64,7 +64,8 @@ __global__ void cs_k_init_ang(uint8_t* arena, size_t stride, size_t ds_off, size
 template <int DT>
 __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_ANG_MIN_BLOCKS) cs_k_simplest(const CsSimplestParams p) {
     const uint32_t lane = cs_lane();
-    const uint32_t worker = blockIdx.x * CS_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const uint32_t wic = threadIdx.x >> 5;  // (the broadcast form, cs_warp_in_cta, costs this kernel 1.6 %)
+    const uint32_t worker = blockIdx.x * CS_WARPS_PER_CTA + wic;
     const uint32_t ltmask = cs_lanemask_lt();
     uint8_t* base = p.arena + (size_t)worker * p.lay.stride;
     uint2* ds = reinterpret_cast<uint2*>(base + p.lay.ds);  // per state {route cost bits, slot | VISITED}
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(CS_WARPS_PER_CTA * 32, CS_ANG_MIN_BLOCKS) cs_k
     uint32_t* pending = reinterpret_cast<uint32_t*>(base + p.lay.pending);
     __shared__ uint2 s_heap[CS_WARPS_PER_CTA][CS_ANG_HEAP_SMEM];
     CsHeap heap;
-    cs_heap_init(heap, s_heap[threadIdx.x >> 5], CS_ANG_HEAP_SMEM, reinterpret_cast<uint2*>(base + p.lay.heap));
+    cs_heap_init(heap, s_heap[wic], CS_ANG_HEAP_SMEM, reinterpret_cast<uint2*>(base + p.lay.heap));
     const uint32_t rcap = p.lay.rcap, hcap = p.lay.hcap;
     const int D = p.D;
     const size_t n = p.n;
