@@ -96,7 +96,10 @@ class BetweennessShortestResult(_ResultBase):
 
 class OdMatrix:
     """Sparse origin-destination trip weights (centrality.rs:54-91): ``{origin: {destination: weight}}`` built from
-    parallel arrays; a repeated (origin, destination) pair keeps the last weight, like the reference's HashMap insert."""
+    parallel arrays; a repeated (origin, destination) pair keeps the last weight, like the reference's HashMap insert.
+
+    Held as three columns sorted by (origin, destination), one row per distinct pair - what the device call consumes
+    (``NetworkStructure._prepare_od``); the nested-dict view ``map`` is built on first use."""
 
     def __init__(self, origins, destinations, weights):
         origins, destinations, weights = list(origins), list(destinations), list(weights)
@@ -105,17 +108,35 @@ class OdMatrix:
                 f"origins ({len(origins)}), destinations ({len(destinations)}), and weights ({len(weights)}) "
                 "must have equal length"
             )
-        self.map: dict[int, dict[int, float]] = {}
-        for o, d, w in zip(origins, destinations, weights):
-            o, d = int(o), int(d)
-            if o < 0 or d < 0:
-                raise OverflowError("can't convert negative int to unsigned")
-            self.map.setdefault(o, {})[d] = float(np.float32(w))
+        o, d = np.asarray(origins), np.asarray(destinations)
+        if not (len(origins) and o.dtype.kind in "iu" and d.dtype.kind in "iu"):
+            # anything but plain integer columns: element by element, with Python's own conversions and errors
+            o = np.asarray([int(x) for x in origins], dtype=object)
+            d = np.asarray([int(x) for x in destinations], dtype=object)
+        if len(origins) and (min(o.min(), d.min()) < 0):
+            raise OverflowError("can't convert negative int to unsigned")
+        o, d = o.astype(np.int64), d.astype(np.int64)
+        w = np.asarray(weights, dtype=np.float32)
+        order = np.lexsort((d, o))  # stable: among equal pairs the input order survives, the last one is kept
+        o, d, w = o[order], d[order], w[order]
+        keep = np.ones(len(o), bool)
+        keep[:-1] = (o[1:] != o[:-1]) | (d[1:] != d[:-1])
+        self._o, self._d, self._w = o[keep], d[keep], w[keep]
+        self._map: dict[int, dict[int, float]] | None = None
+
+    @property
+    def map(self) -> dict[int, dict[int, float]]:
+        if self._map is None:
+            m: dict[int, dict[int, float]] = {}
+            for o, d, w in zip(self._o.tolist(), self._d.tolist(), self._w.tolist()):
+                m.setdefault(o, {})[d] = w
+            self._map = m
+        return self._map
 
     def len(self) -> int:
         """Number of non-zero OD pairs."""
-        return sum(len(d) for d in self.map.values())
+        return int(len(self._o))
 
     def n_origins(self) -> int:
         """Number of unique origin nodes."""
-        return len(self.map)
+        return int(len(np.unique(self._o)))

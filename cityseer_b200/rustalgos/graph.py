@@ -848,25 +848,26 @@ class NetworkStructure:
         blocks hold about the same number of trips."""
         f = self.frozen()
         live = f.live.astype(bool) & f.node_exists.astype(bool)
-        origins = [o for o in sorted(od_matrix.map) if 0 <= o < f.node_bound and live[o] and od_matrix.map[o]]
-        if shard is not None and origins:
+        o, d, w = od_matrix._o, od_matrix._d, od_matrix._w  # sorted by (origin, destination), pairs distinct
+        ok = o < f.node_bound
+        ok[ok] = live[o[ok]]
+        o, d, w = o[ok], d[ok], w[ok]
+        if len(d) and d.max() >= f.node_bound:  # checked on the whole list, so that every rank of a sharded call raises
+            raise ValueError(f"OD destination {int(d[d >= f.node_bound][0])} is out of range for node_bound {f.node_bound}")
+        origins, counts = np.unique(o, return_counts=True)
+        ends = np.cumsum(counts)
+        lo, hi = 0, len(origins)
+        if shard is not None and len(origins):
             rank, world_size = shard
-            ends = np.cumsum([len(od_matrix.map[o]) for o in origins])
             cuts = np.searchsorted(ends, ends[-1] * np.arange(1, world_size) / world_size, side="left") + 1
             cuts = np.concatenate([[0], np.minimum(cuts, len(origins)), [len(origins)]])
-            origins = origins[int(cuts[rank]):int(cuts[rank + 1])]
-        od_off = np.zeros(len(origins) + 1, np.uint64)
-        od_dst, od_w = [], []
-        for k, o in enumerate(origins):
-            dests = od_matrix.map[o]
-            od_dst.extend(dests.keys())
-            od_w.extend(dests.values())
-            od_off[k + 1] = len(od_dst)
-        od_dst = np.asarray(od_dst, np.int64)
-        if len(od_dst) and (od_dst.min() < 0 or od_dst.max() >= f.node_bound):
-            bad = int(od_dst[(od_dst < 0) | (od_dst >= f.node_bound)][0])
-            raise ValueError(f"OD destination {bad} is out of range for node_bound {f.node_bound}")
-        return np.asarray(origins, np.uint32), od_off, od_dst.astype(np.uint32), np.asarray(od_w, np.float32)
+            lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+        first = int(ends[lo - 1]) if lo > 0 else 0
+        last = int(ends[hi - 1]) if hi > 0 else 0
+        od_off = np.zeros(hi - lo + 1, np.uint64)
+        od_off[1:] = ends[lo:hi] - first
+        return (origins[lo:hi].astype(np.uint32), od_off, np.ascontiguousarray(d[first:last], dtype=np.uint32),
+                np.ascontiguousarray(w[first:last], dtype=np.float32))  # fmt: skip
 
     def betweenness_od_shortest(
         self,

@@ -287,3 +287,28 @@ def test_od_lists_and_their_shards():
     # a dead origin is skipped, like the reference's is_node_live check (centrality.rs:2473)
     ns.set_node_live(idx[3], False)
     assert idx[3] not in ns._prepare_od(od)[0].tolist()
+
+
+def test_od_matrix_columns_equal_the_insert_loop():
+    """The columnar OdMatrix (sorted distinct pairs, last weight wins) against the plain HashMap-insert loop it restates
+    (centrality.rs:66-80), for list, numpy and float-valued index inputs."""
+    from cityseer_b200.rustalgos.centrality import OdMatrix
+
+    rng = np.random.default_rng(8)
+    o = rng.integers(0, 40, 3000)
+    d = rng.integers(0, 60, 3000)  # many repeated pairs
+    w = rng.uniform(0, 9, 3000)
+    ref: dict[int, dict[int, float]] = {}
+    for a, b, c in zip(o.tolist(), d.tolist(), w.tolist()):
+        ref.setdefault(a, {})[b] = float(np.float32(c))
+    for od in (OdMatrix(o.tolist(), d.tolist(), w.tolist()), OdMatrix(o, d, w.astype(np.float32)),
+               OdMatrix(o.astype(np.uint32), d.astype(np.int16), w), OdMatrix(o.astype(float).tolist(), d.tolist(), w.tolist())):  # fmt: skip
+        assert od.map == ref
+        assert od.len() == sum(len(x) for x in ref.values()) and od.n_origins() == len(ref)
+        assert np.all(np.diff(od._o) >= 0) and od._w.dtype == np.float32
+    with pytest.raises(OverflowError):
+        OdMatrix([3, 4], [1, -2], [1.0, 1.0])
+    with pytest.raises((TypeError, ValueError)):
+        OdMatrix(["a"], [1], [1.0])
+    empty = OdMatrix([], [], [])
+    assert empty.len() == 0 and empty.n_origins() == 0 and empty.map == {}
