@@ -27,7 +27,7 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:cs_k
 for tool in memcheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_segment.py tests/test_gpu_simplest.py tests/test_gpu_tree.py \
       "tests/test_gpu_chain.py::test_segment_decomposed_grid" "tests/test_gpu_chain.py::test_segment_regular_grid_is_replayed_in_heap_order" \
-      "tests/test_gpu_chain.py::test_decomposed_grid_with_tolerance" tests/test_gpu_slope_transport.py -m gpu -q -x -p no:cacheprovider \
+      "tests/test_gpu_chain.py::test_decomposed_grid_with_tolerance" tests/test_gpu_slope_transport.py tests/test_gpu_od.py -m gpu -q -x -p no:cacheprovider \
       > gpurun_out/${tag}_sanitizer_$tool.log 2>&1
   echo "$tool rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/${tag}_sanitizer_$tool.log | tail -3
 done
